@@ -1,0 +1,261 @@
+/*
+ * megatts2_b200.h - C ABI of libmegatts2_b200.so (sm_100a).
+ *
+ * The reference (LSimon95/megatts2 @ 2ab81a1) has no FFI layer: its replaceable surface
+ * is the Python nn.Module API.  This library is what those modules bind
+ * through ctypes; every entry point names the reference function it replaces
+ * (file:line relative to the reference repo).
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; fp32 unless stated
+ *  - activations are channels-last: (B, T, C) with an explicit row stride `ld` (elements)
+ *    and batch stride; the Python layer converts from/to the reference's (B, C, T)
+ *  - the caller owns every buffer (inputs, outputs, workspace); the library never
+ *    allocates device memory and keeps no pointer after return
+ *  - work is enqueued on `stream` (a cudaStream_t passed as void*); no hidden device sync
+ *  - every function returns 0 on success or a negative mtts_status; mtts_last_error()
+ *    returns a thread-local message.  There is NO CPU fallback anywhere.
+ */
+#ifndef MEGATTS2_B200_H
+#define MEGATTS2_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTTS_ABI_VERSION 1
+
+typedef enum {
+  MTTS_OK = 0,
+  MTTS_ERR_BAD_ARG = -1,
+  MTTS_ERR_UNSUPPORTED = -2,
+  MTTS_ERR_CUDA = -3,
+  MTTS_ERR_WORKSPACE = -4
+} mtts_status;
+
+int mtts_abi_version(void);
+const char* mtts_last_error(void);
+/* number of kernels this library has launched in this process (bench.py gpu_launches) */
+int64_t mtts_launch_count(void);
+/* measurement aid (bench.py roofline leg; off by default): between begin and end every
+ * tap-GEMM launch is bracketed by CUDA events on its stream; end() synchronises and returns
+ * the summed kernel time, the summed algorithmic FLOPs (2*M*N*Cin*k) and the launch count. */
+int mtts_profile_begin(void);
+int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+
+/* activation / padding codes */
+enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };
+enum { MTTS_PAD_ZERO = 0, MTTS_PAD_REFLECT = 1, MTTS_PAD_REPLICATE = 2 };
+
+/* ------------------------------------------------------------------------------------------
+ * Tap-GEMM: the one dense contraction of the path.  Covers nn.Linear (k = 1), nn.Conv1d
+ * (modules/convnet.py:13-18,88-94; modules/transformer.py:76-78; modules/mrte.py:101-107
+ * stride 16), dilated HiFi-GAN convs and ConvTranspose1d (as a 2-tap conv with s*Cout
+ * columns):
+ *   acc[b,t,n] = sum_{j<k} sum_{c<Cin} pre(X[b, t*stride + j*dil - pad, c]) * W[j][c][n]
+ *   v = post(acc + bias[n]);  v += R[b,t,n];  v *= out_scale;  v += Y_old (accumulate)
+ *   Y[b, t*ldy + n + out_shift] = v        (skipped when outside [0, y_batch_elems))
+ * W is PRE-PACKED as (k, Cin, Cout) row-major (mtts_pack_* on the host side does that once).
+ */
+typedef struct {
+  const float* x; int64_t x_batch_stride; int32_t ldx;
+  const float* w;
+  const float* bias;                       /* (Cout) or NULL */
+  const float* res; int64_t res_batch_stride; int32_t ldr;   /* optional */
+  float* y; int64_t y_batch_stride; int32_t ldy;
+  int32_t B, Tin, Tout, Cin, Cout;
+  int32_t k, stride, dil, pad;
+  int32_t pad_mode;                        /* MTTS_PAD_* */
+  int32_t pre_act; float pre_slope;        /* applied to X on load */
+  int32_t post_act; float post_slope;
+  float out_scale;
+  int32_t accumulate;
+  int64_t out_shift;                       /* 0 for ordinary convs */
+  int64_t y_batch_elems;                   /* 0 -> Tout*ldy */
+  const int32_t* in_lens;                  /* optional (B): rows >= len read as zero / reflect about len */
+} mtts_conv_params;
+
+int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);
+
+/* LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; modules/convnet.py:28-30,
+ * modules/transformer.py:67-68, modules/mrte.py:136):
+ *   v = LN(x[row]) * gamma + beta;  v = post(v);  v += res[row];  v += y_old (accumulate) */
+int mtts_layernorm_f32(const float* x, int32_t ldx, const float* gamma, const float* beta,
+                       const float* res, int32_t ldr, float* y, int32_t ldy,
+                       int64_t rows, int32_t C, float eps, int32_t post_act, int32_t accumulate,
+                       void* stream);
+
+/* softmax(Q K^T * scale + mask) V  (F.scaled_dot_product_attention at
+ * modules/transformer.py:52-53).  q/k/v/o are (B, T, H, dh) views given by strides;
+ * mask is additive fp32 with element strides (mask_sb, mask_sh, mask_sq, 1) or NULL.
+ * dh in {64, 96, 128, 256, 512}.  q_row0/n_q select a row range of the queries. */
+typedef struct {
+  const float* q; int64_t q_sb; int32_t q_st;
+  const float* k; int64_t k_sb; int32_t k_st;
+  const float* v; int64_t v_sb; int32_t v_st;
+  float* o; int64_t o_sb; int32_t o_st;
+  const float* mask; int64_t mask_sb, mask_sh, mask_sq;
+  int32_t B, H, Tq, Tk, dh;
+  float scale;
+} mtts_attn_params;
+int mtts_attention_f32(const mtts_attn_params* p, void* stream);
+
+/* EuclideanCodebook.quantize (modules/quantization/core_vq.py:175-183): first index of
+ * max_k -(|x|^2 - 2 x.e_k + |e_k|^2).  x (N, D) ld = ldx, embed (K, D) -> idx (N) int64 */
+int mtts_vq_argmin_f32(const float* x, int32_t ldx, const float* embed, int64_t N, int32_t D, int32_t K,
+                       int64_t* idx, void* stream);
+/* EuclideanCodebook.dequantize / ResidualVectorQuantizer.decode (core_vq.py:188-190, 360-367)
+ * with an optional time-repeat (vqpe.py:60-61, models/megatts2.py:362-364):
+ *   y[b, t, :] = embed[idx[b, t / repeat], :]  for t < T_out;  y is (B, T_out, ldy) */
+int mtts_vq_gather_f32(const int64_t* idx, int32_t idx_ld, const float* embed, int32_t D, int32_t K,
+                       int32_t B, int32_t T_out, int32_t repeat, float* y, int64_t y_sb, int32_t ldy,
+                       void* stream);
+
+/* extract_mel_spec (modules/tokenizer.py:107-125): reflect-padded
+ * 1024-point STFT (hop 256, window table given), magnitude, banded mel filterbank,
+ * log(max(., clamp)).  wav (B, L) -> out[b*out_sb + m*out_sm + f*out_sf], f < 1 + L/256.
+ * The filterbank is passed in banded form: for mel m, taps fb_w[fb_off[m] .. fb_off[m+1])
+ * apply to bins fb_start[m] ...   n_fft must be 1024, hop 256. */
+int mtts_mel_spectrogram_f32(const float* wav, int64_t wav_sb, int32_t B, int32_t L,
+                             const float* window, const float* fb_w, const int32_t* fb_off,
+                             const int32_t* fb_start, int32_t n_mels, float clamp_min,
+                             float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, void* stream);
+
+/* nn.MaxPool1d(k, ceil_mode=True) over time, channels-last (modules/vqpe.py:38,
+ * models/megatts2.py:357-358).  x (B, T, C) -> y (B, ceil(T/k), C) */
+int mtts_maxpool_time_f32(const float* x, int64_t x_sb, int32_t ldx, float* y, int64_t y_sb, int32_t ldy,
+                          int32_t B, int32_t T, int32_t C, int32_t k, void* stream);
+
+/* TokenEmbedding + SinePositionalEmbedding (modules/embedding.py:41-47, 94-98):
+ *   y[b,t,:] = table[ids[b,t],:] + alpha * pe[t + pe_offset,:]    (pe may be NULL) */
+int mtts_embed_pe_f32(const int64_t* ids, int32_t ids_ld, const float* table, int32_t vocab, int32_t D,
+                      const float* pe, float alpha, int32_t pe_offset, int32_t B, int32_t T,
+                      float* y, int64_t y_sb, int32_t ldy, void* stream);
+/* y = x + alpha * pe[t,:]  (SinePositionalEmbedding.forward on an existing tensor) */
+int mtts_add_pe_f32(const float* x, int64_t x_sb, int32_t ldx, const float* pe, float alpha,
+                    int32_t B, int32_t T, int32_t D, float* y, int64_t y_sb, int32_t ldy, void* stream);
+
+/* LengthRegulator.forward (modules/mrte.py:23-31, 42-60) as a gather:
+ *   y[b, sum_{j<i} d[b,j] + r, :] = x[b,i,:]; rows >= sum(d[b]) are zero.
+ * totals (B) int32 receives sum(d[b]) (pass NULL to skip). y is (B, L_out, ldy). */
+int mtts_length_regulate_f32(const float* x, int64_t x_sb, int32_t ldx, const int32_t* dur, int32_t dur_ld,
+                             int32_t B, int32_t Tp, int32_t D, int32_t L_out,
+                             float* y, int64_t y_sb, int32_t ldy, int32_t* totals, void* stream);
+
+/* strided 2-D copy / transpose helpers used at the (B,C,T) <-> (B,T,C) module boundary:
+ *   y[b, t, c] = x[b*x_sb + t*x_st + c*x_sc]   with optional replicate padding of `pad`
+ *   rows at both ends of t (HiFi-GAN inference_padding) */
+int mtts_copy_strided_f32(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc,
+                          float* y, int64_t y_sb, int64_t y_st, int64_t y_sc,
+                          int32_t B, int32_t T, int32_t C, int32_t pad_rep, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Composite drivers: whole sub-networks enqueued by one call (C++ launch loop, no Python
+ * per-kernel overhead).  Weight pointers refer to PRE-PACKED device buffers owned by the
+ * caller.
+ */
+typedef struct {
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const float *w_qkv, *b_qkv;          /* (1, D, 3D) packed, (3D) */
+  const float *w_o, *b_o;              /* (1, D, D), (D) */
+  const float *w_ff1, *b_ff1;          /* linear: (1, D, F); conv-FF: (5, D, F) */
+  const float *w_ff2, *b_ff2;          /* linear: (1, F, D); conv-FF: (5, F, D) */
+} mtts_encoder_layer;
+
+typedef struct {
+  int32_t n_layers, d_model, n_heads, ff_dim, conv_ff;
+  const mtts_encoder_layer* layers;    /* HOST array of n_layers entries */
+} mtts_encoder;
+
+/* TransformerEncoder.forward (modules/transformer.py:119-133).  x (B,T,D) -> y (B,T,D);
+ * mask: optional additive (B,H,T,T) fp32 (utils/utils.py:21-39) given by strides.
+ * last_row_only != 0: y is (B,1,D) = the last position's output (exact pruning of the final
+ * layer; what MegaPLM.infer / MegaADM.infer consume, models/megatts2.py:178, 272). */
+int64_t mtts_encoder_workspace_bytes(const mtts_encoder* enc, int32_t B, int32_t T);
+int mtts_encoder_forward_f32(const mtts_encoder* enc, const float* x, float* y, int32_t B, int32_t T,
+                             const float* mask, int64_t mask_sb, int64_t mask_sh, int64_t mask_sq,
+                             int32_t last_row_only, void* workspace, int64_t workspace_bytes, void* stream);
+
+/* MegaPLM.infer (models/megatts2.py:165-181): greedy AR decode, BOS = vq_bins, exactly T
+ * steps, NON-causal full recompute per step (reference-faithful).  tc_latent (B,T,tc_dim);
+ * codes_out (B,T) int64; logits_out optional (B,T,vq_bins) = last-position logits per step. */
+typedef struct {
+  mtts_encoder enc;
+  const float* pc_embedding;   /* (vq_bins+2, vq_dim) */
+  const float* w_predict;      /* packed (1, D, vq_bins) */
+  const float* pe;             /* (>=T, D) sine table (modules/embedding.py:66-92) */
+  float pe_alpha;
+  int32_t vq_bins, vq_dim, tc_dim;
+} mtts_plm;
+int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T);
+int mtts_plm_infer_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld,
+                       int32_t B, int32_t T, int64_t* codes_out, float* logits_out,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* MegaADM.infer (models/megatts2.py:257-275): AR duration regression, raw float feedback,
+ * final (p + 0.5) -> int32 -> clamp(1,128).  dur_out (B,T) int32; raw_out optional (B,T). */
+typedef struct {
+  mtts_encoder enc;
+  const float* w_dt;           /* (emb_dim)   dt_linear_emb.weight[:,0] */
+  const float* w_tc;           /* packed (1, tc_dim, tc_emb_dim) */
+  const float* w_predict;      /* (D) predict_layer.weight[0,:] */
+  const float* pe; float pe_alpha;
+  int32_t emb_dim, tc_dim, tc_emb_dim;
+} mtts_adm;
+int64_t mtts_adm_infer_workspace_bytes(const mtts_adm* m, int32_t B, int32_t T);
+int mtts_adm_infer_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld,
+                       int32_t B, int32_t T, int32_t* dur_out, float* raw_out,
+                       void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ConvNet family (modules/convnet.py).  One ConvBlock = ReLU -> Conv1d(C,C,k,same) -> LN(C). */
+typedef struct { const float *w, *b, *ln_g, *ln_b; } mtts_conv_block;   /* w packed (k,C,C) */
+
+typedef struct {
+  int32_t in_channels, out_channels, hidden, k, n_stacks, n_blocks;
+  const float *w_first, *b_first;      /* packed (k, Cin, hidden) */
+  const float *w_last, *b_last;        /* packed (k, hidden, Cout) */
+  const mtts_conv_block* blocks;       /* HOST array [n_stacks*n_blocks] */
+} mtts_convnet;
+/* ConvNet.forward (convnet.py:115-119): x (B,T,Cin) -> y (B,T,Cout), channels-last */
+int64_t mtts_convnet_workspace_bytes(const mtts_convnet* n, int32_t B, int32_t T);
+int mtts_convnet_forward_f32(const mtts_convnet* n, const float* x, int64_t x_sb, int32_t ldx,
+                             float* y, int64_t y_sb, int32_t ldy, int32_t B, int32_t T,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+typedef struct {
+  int32_t in_channels, out_channels, hidden, k, n_layers, n_stacks, n_blocks;
+  int32_t middle_kind;                 /* 0: MaxPool1d(middle_k, ceil) ; 1: strided Conv1d(k=middle_k, stride, pad) */
+  int32_t middle_k, middle_stride, middle_pad;
+  const float *w_middle, *b_middle;    /* packed (middle_k, hidden, hidden) when middle_kind == 1 */
+  const float *w_first, *b_first, *w_last, *b_last;
+  const mtts_conv_block* blocks;       /* HOST array [n_layers][2][n_stacks*n_blocks] */
+} mtts_convnet_double;
+/* ConvNetDouble.forward (convnet.py:202-210): x (B,T,Cin) -> y (B,T_mid,Cout) */
+int32_t mtts_convnet_double_out_len(const mtts_convnet_double* n, int32_t T);
+int64_t mtts_convnet_double_workspace_bytes(const mtts_convnet_double* n, int32_t B, int32_t T);
+int mtts_convnet_double_forward_f32(const mtts_convnet_double* n, const float* x, int64_t x_sb, int32_t ldx,
+                                    float* y, int64_t y_sb, int32_t ldy, int32_t B, int32_t T,
+                                    void* workspace, int64_t workspace_bytes, void* stream);
+
+/* HiFi-GAN V1 generator (speechbrain HIFIGAN.decode_batch, called at
+ * models/megatts2.py:370-372).  mel (B, T, 80) channels-last -> wav (B, 256*(T+2*pad)). */
+typedef struct { const float *w1[3], *b1[3], *w2[3], *b2[3]; int32_t k; int32_t dil[3]; } mtts_hifigan_resblock;
+typedef struct {
+  int32_t in_channels, ch0, n_ups, n_kernels, inference_padding;
+  int32_t up_factor[4], up_kernel[4];
+  const float *w_pre, *b_pre;          /* packed (7, 80, ch0) */
+  const float *w_up[4], *b_up[4];      /* packed (2, Cin, s*Cout), bias expanded to (s*Cout) */
+  const mtts_hifigan_resblock* resblocks;  /* HOST array [n_ups*n_kernels] */
+  const float *w_post, *b_post;        /* packed (7, C_last, 1) */
+} mtts_hifigan;
+int64_t mtts_hifigan_workspace_bytes(const mtts_hifigan* h, int32_t B, int32_t T);
+int mtts_hifigan_forward_f32(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int32_t mel_ld,
+                             int32_t B, int32_t T, float* wav, int64_t wav_sb,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MEGATTS2_B200_H */

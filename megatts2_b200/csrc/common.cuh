@@ -1,0 +1,76 @@
+// Shared helpers for libmegatts2_b200 (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <atomic>
+
+#include "../../include/megatts2_b200.h"
+
+namespace mtts {
+
+extern thread_local char g_err[512];
+extern std::atomic<int64_t> g_launches;
+
+inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, long long c = 0) {
+  snprintf(g_err, sizeof(g_err), fmt, a, b, c);
+  return code;
+}
+
+#define MTTS_REQUIRE(cond, msg)                                                      \
+  do {                                                                               \
+    if (!(cond)) return mtts::fail(MTTS_ERR_BAD_ARG, "%s: requirement failed: " msg, __func__); \
+  } while (0)
+
+#define MTTS_CHECK_LAUNCH()                                                          \
+  do {                                                                               \
+    mtts::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    cudaError_t e__ = cudaGetLastError();                                            \
+    if (e__ != cudaSuccess)                                                          \
+      return mtts::fail(MTTS_ERR_CUDA, "%s: CUDA launch failed: %lld", __func__, (long long)e__); \
+  } while (0)
+
+#define MTTS_TRY(expr)                                                               \
+  do {                                                                               \
+    int r__ = (expr);                                                                \
+    if (r__ != 0) return r__;                                                        \
+  } while (0)
+
+static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
+static inline int64_t align_up(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
+
+// bump allocator over the caller-provided workspace
+struct Arena {
+  char* base;
+  int64_t size, off;
+  Arena(void* p, int64_t n) : base((char*)p), size(n), off(0) {}
+  template <typename T>
+  T* take(int64_t n) {
+    off = align_up(off, 256);
+    T* r = (T*)(base + off);
+    off += n * (int64_t)sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= size; }
+};
+
+__device__ __forceinline__ float act_apply(float v, int act, float slope) {
+  if (act == MTTS_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == MTTS_ACT_LEAKY) return v > 0.f ? v : v * slope;
+  if (act == MTTS_ACT_TANH) return tanhf(v);
+  return v;
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+}  // namespace mtts

@@ -1,0 +1,509 @@
+// Composite drivers: whole sub-networks of the synthesis path enqueued from C++ (no Python
+// per-kernel overhead, no host sync inside).  Buffers come from the caller's workspace.
+#include <mutex>
+#include <vector>
+
+#include "kernels.h"
+
+namespace mtts {
+
+// Optional per-launch timing of the tap-GEMM kernels (bench.py's roofline leg): CUDA events on
+// the launching stream around every conv1d launch; off by default, never on the timed path.
+struct ProfRec { cudaEvent_t a, b; double flops; };
+static std::mutex g_prof_mu;
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+
+int conv1d(const mtts_conv_params& p, cudaStream_t st) {
+  if (!g_prof_on) return conv1d_ffma(p, st);
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  ProfRec r;
+  if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess)
+    return fail(MTTS_ERR_CUDA, "%s: cudaEventCreate failed", "profile");
+  r.flops = 2.0 * (double)p.B * p.Tout * p.Cout * p.Cin * p.k;
+  cudaEventRecord(r.a, st);
+  const int rc = conv1d_ffma(p, st);
+  cudaEventRecord(r.b, st);
+  g_prof.push_back(r);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------
+// TransformerEncoder.forward (modules/transformer.py:88-102, 119-133)
+static int64_t encoder_ws_floats(const mtts_encoder* e, int B, int T) {
+  const int64_t M = (int64_t)B * T, D = e->d_model, F = e->ff_dim;
+  // xw, h, qkv(3D), a, f  (+ alignment slack)
+  return M * (D + D + 3 * D + D + F) + 5 * 64;
+}
+
+static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int B, int T, const float* mask,
+                           int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, int last_row_only, Arena& ar,
+                           cudaStream_t st) {
+  const int D = e->d_model, H = e->n_heads, F = e->ff_dim, dh = D / H;
+  MTTS_REQUIRE(D % H == 0, "d_model not divisible by n_heads");
+  MTTS_REQUIRE(!(last_row_only && e->conv_ff), "last_row_only needs a linear feed-forward");
+  MTTS_REQUIRE(e->n_layers >= 1, "no layers");
+  const int64_t M = (int64_t)B * T;
+  if (M == 0) return 0;
+  float* xw = last_row_only ? ar.take<float>(M * D) : y;   // running activations (B,T,D)
+  float* h = ar.take<float>(M * D);
+  float* qkv = ar.take<float>(M * 3 * D);
+  float* a = ar.take<float>(M * D);
+  float* f = ar.take<float>(M * F);
+  if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "encoder", ar.off);
+  const float scale = 1.0f / sqrtf((float)dh);
+  const float* xin = x;
+  for (int l = 0; l < e->n_layers; ++l) {
+    const mtts_encoder_layer& L = e->layers[l];
+    const bool last = last_row_only && (l == e->n_layers - 1);
+    // h = LN1(x);  qkv = h Wqkv + b
+    MTTS_TRY(layernorm(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
+    {
+      mtts_conv_params p = linear_params(h, D, L.w_qkv, L.b_qkv, qkv, 3 * D, M, D, 3 * D);
+      MTTS_TRY(conv1d(p, st));
+    }
+    mtts_attn_params ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.B = B; ap.H = H; ap.Tk = T; ap.dh = dh; ap.scale = scale;
+    ap.k = qkv + D; ap.k_sb = (int64_t)T * 3 * D; ap.k_st = 3 * D;
+    ap.v = qkv + 2 * D; ap.v_sb = (int64_t)T * 3 * D; ap.v_st = 3 * D;
+    ap.mask = mask; ap.mask_sb = mask_sb; ap.mask_sh = mask_sh; ap.mask_sq = mask_sq;
+    if (!last) {
+      ap.q = qkv; ap.q_sb = (int64_t)T * 3 * D; ap.q_st = 3 * D; ap.Tq = T;
+      ap.o = a; ap.o_sb = (int64_t)T * D; ap.o_st = D;
+      MTTS_TRY(attention(ap, st));
+      // x = x + a Wo + bo
+      mtts_conv_params p = linear_params(a, D, L.w_o, L.b_o, xw, D, M, D, D);
+      p.res = xin; p.ldr = D;
+      MTTS_TRY(conv1d(p, st));
+      if (e->conv_ff) {
+        // x = LN2(x); x = x + conv5(relu(conv5(x)))       (transformer.py:96-98)
+        MTTS_TRY(layernorm(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, xw, D, M, D, 1e-5f, 0, 0, st));
+        mtts_conv_params c1 = conv_same_params(xw, L.w_ff1, L.b_ff1, f, B, T, D, F, 5, 1, MTTS_PAD_ZERO);
+        c1.post_act = MTTS_ACT_RELU;
+        MTTS_TRY(conv1d(c1, st));
+        mtts_conv_params c2 = conv_same_params(f, L.w_ff2, L.b_ff2, xw, B, T, F, D, 5, 1, MTTS_PAD_ZERO);
+        c2.res = xw; c2.res_batch_stride = (int64_t)T * D; c2.ldr = D;
+        MTTS_TRY(conv1d(c2, st));
+      } else {
+        // x = x + W2 relu(W1 LN2(x) + b1) + b2             (transformer.py:101)
+        MTTS_TRY(layernorm(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
+        mtts_conv_params p1 = linear_params(h, D, L.w_ff1, L.b_ff1, f, F, M, D, F);
+        p1.post_act = MTTS_ACT_RELU;
+        MTTS_TRY(conv1d(p1, st));
+        mtts_conv_params p2 = linear_params(f, F, L.w_ff2, L.b_ff2, xw, D, M, F, D);
+        p2.res = xw; p2.ldr = D;
+        MTTS_TRY(conv1d(p2, st));
+      }
+      xin = xw;
+    } else {
+      // final layer, last position only (exact: nothing else is consumed downstream)
+      ap.q = qkv + (int64_t)(T - 1) * 3 * D; ap.q_sb = (int64_t)T * 3 * D; ap.q_st = 3 * D; ap.Tq = 1;
+      if (mask) ap.mask = mask + (int64_t)(T - 1) * mask_sq;
+      ap.o = a; ap.o_sb = D; ap.o_st = D;
+      MTTS_TRY(attention(ap, st));
+      mtts_conv_params p;
+      memset(&p, 0, sizeof(p));
+      p.x = a; p.ldx = D; p.x_batch_stride = D;
+      p.w = L.w_o; p.bias = L.b_o;
+      p.res = xin + (int64_t)(T - 1) * D; p.res_batch_stride = (int64_t)T * D; p.ldr = D;
+      p.y = y; p.ldy = D; p.y_batch_stride = D;
+      p.B = B; p.Tin = 1; p.Tout = 1; p.Cin = D; p.Cout = D; p.k = 1; p.stride = 1; p.dil = 1;
+      p.out_scale = 1.0f;
+      MTTS_TRY(conv1d(p, st));
+      MTTS_TRY(layernorm(y, D, L.ln2_g, L.ln2_b, nullptr, 0, h, D, B, D, 1e-5f, 0, 0, st));
+      mtts_conv_params p1 = linear_params(h, D, L.w_ff1, L.b_ff1, f, F, B, D, F);
+      p1.post_act = MTTS_ACT_RELU;
+      MTTS_TRY(conv1d(p1, st));
+      mtts_conv_params p2 = linear_params(f, F, L.w_ff2, L.b_ff2, y, D, B, F, D);
+      p2.res = y; p2.ldr = D;
+      MTTS_TRY(conv1d(p2, st));
+    }
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MegaPLM.infer (models/megatts2.py:165-181)
+static int64_t plm_ws_floats(const mtts_plm* m, int B, int T) {
+  const int64_t D = m->enc.d_model;
+  return encoder_ws_floats(&m->enc, B, T) + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * m->vq_bins +
+         2 * ((int64_t)B * (T + 1) + 64) + 6 * 64;
+}
+
+static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_ld, int B, int T, int64_t* codes_out,
+                     float* logits_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int D = m->enc.d_model, V = m->vq_bins;
+  MTTS_REQUIRE(D == m->tc_dim + m->vq_dim, "d_model != tc_dim + vq_dim");
+  MTTS_REQUIRE(tc && codes_out && m->pc_embedding && m->w_predict && m->pe, "null pointer");
+  if (B <= 0 || T <= 0) return 0;
+  Arena top(ws, ws_bytes);
+  float* X = top.take<float>((int64_t)B * T * D);
+  float* xl = top.take<float>((int64_t)B * D);
+  float* logits = top.take<float>((int64_t)B * V);
+  int64_t* codes = top.take<int64_t>((int64_t)B * (T + 1));
+  const int64_t enc_off = align_up(top.off, 256);
+  if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
+    return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "plm_infer",
+                enc_off + encoder_ws_floats(&m->enc, B, T) * 4);
+  MTTS_TRY(fill_i64(codes, T + 1, B, (int64_t)V, st));   // BOS = vq_bins (megatts2.py:170-171)
+  for (int t = 0; t < T; ++t) {
+    const int S = t + 1;
+    MTTS_TRY(plm_build_input(tc, tc_sb, tc_ld, m->tc_dim, codes, T + 1, m->pc_embedding, m->vq_dim, V + 2, m->pe,
+                             m->pe_alpha, B, S, X, st));
+    Arena ar((char*)ws + enc_off, ws_bytes - enc_off);
+    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, st));
+    float* lg = logits_out ? logits_out + (int64_t)t * V : logits;
+    const int64_t lg_sb = logits_out ? (int64_t)T * V : V;
+    mtts_conv_params p;
+    memset(&p, 0, sizeof(p));
+    p.x = xl; p.ldx = D; p.x_batch_stride = D;
+    p.w = m->w_predict;
+    p.y = lg; p.ldy = V; p.y_batch_stride = lg_sb;
+    p.B = B; p.Tin = 1; p.Tout = 1; p.Cin = D; p.Cout = V; p.k = 1; p.stride = 1; p.dil = 1; p.out_scale = 1.0f;
+    MTTS_TRY(conv1d(p, st));
+    MTTS_TRY(argmax_rows(lg, lg_sb, V, B, codes + (t + 1), T + 1, codes_out + t, T, st));
+  }
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// MegaADM.infer (models/megatts2.py:257-275)
+static int64_t adm_ws_floats(const mtts_adm* m, int B, int T) {
+  const int64_t D = m->enc.d_model;
+  return encoder_ws_floats(&m->enc, B, T) + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * T * m->tc_emb_dim +
+         (int64_t)B * (T + 1) + 6 * 64;
+}
+
+static int adm_infer(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_ld, int B, int T, int32_t* dur_out,
+                     float* raw_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int D = m->enc.d_model;
+  MTTS_REQUIRE(D == m->emb_dim + m->tc_emb_dim, "d_model != emb_dim + tc_emb_dim");
+  MTTS_REQUIRE(tc && dur_out && m->w_dt && m->w_tc && m->w_predict && m->pe, "null pointer");
+  if (B <= 0 || T <= 0) return 0;
+  Arena top(ws, ws_bytes);
+  float* X = top.take<float>((int64_t)B * T * D);
+  float* xl = top.take<float>((int64_t)B * D);
+  float* tc_emb = top.take<float>((int64_t)B * T * m->tc_emb_dim);
+  float* praw = top.take<float>((int64_t)B * (T + 1));
+  const int64_t enc_off = align_up(top.off, 256);
+  if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
+    return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "adm_infer",
+                enc_off + encoder_ws_floats(&m->enc, B, T) * 4);
+  // tc_linear_emb(tc_latents[:, :t+1]) is step-invariant row by row: computed once (exact)
+  {
+    mtts_conv_params p;
+    memset(&p, 0, sizeof(p));
+    p.x = tc; p.ldx = tc_ld; p.x_batch_stride = tc_sb;
+    p.w = m->w_tc;
+    p.y = tc_emb; p.ldy = m->tc_emb_dim; p.y_batch_stride = (int64_t)T * m->tc_emb_dim;
+    p.B = B; p.Tin = T; p.Tout = T; p.Cin = m->tc_dim; p.Cout = m->tc_emb_dim; p.k = 1; p.stride = 1; p.dil = 1;
+    p.out_scale = 1.0f;
+    MTTS_TRY(conv1d(p, st));
+  }
+  MTTS_TRY(fill_f32(praw, T + 1, B, 0.0f, st));   // p_code = [[0]] (megatts2.py:262-263)
+  for (int t = 0; t < T; ++t) {
+    const int S = t + 1;
+    MTTS_TRY(adm_build_input(tc_emb, (int64_t)T * m->tc_emb_dim, m->tc_emb_dim, m->tc_emb_dim, praw, T + 1, m->w_dt,
+                             m->emb_dim, m->pe, m->pe_alpha, B, S, X, st));
+    Arena ar((char*)ws + enc_off, ws_bytes - enc_off);
+    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, st));
+    MTTS_TRY(adm_readout(xl, D, m->w_predict, B, praw, T + 1, t + 1, st));
+  }
+  MTTS_TRY(adm_finalize(praw, T + 1, B, T, dur_out, raw_out, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// ConvNet family (modules/convnet.py), channels-last
+struct StackBufs { float *tmp, *h1; };
+
+// ResidualBlockStack.forward (convnet.py:69-72): x = x + ConvStack(x), n_stacks times.
+// Reads `src` (never written), leaves the result in `dst` (may equal src); if final_dst is
+// given, the LAST stack writes (x + y) there instead (optionally accumulating).
+static int residual_stack(const mtts_conv_block* blocks, int n_stacks, int n_blocks, int C, int k, int B, int T,
+                          const float* src, float* dst, float* final_dst, int final_accumulate, const StackBufs& sb,
+                          cudaStream_t st) {
+  const int64_t M = (int64_t)B * T;
+  const float* cur = src;
+  for (int s = 0; s < n_stacks; ++s) {
+    const float* yin = cur;
+    for (int b = 0; b < n_blocks; ++b) {
+      const mtts_conv_block& bl = blocks[s * n_blocks + b];
+      // ConvBlock (convnet.py:22-31): ReLU -> conv -> LN
+      mtts_conv_params p = conv_same_params(yin, bl.w, bl.b, sb.tmp, B, T, C, C, k, 1, MTTS_PAD_ZERO);
+      p.pre_act = MTTS_ACT_RELU;
+      MTTS_TRY(conv1d(p, st));
+      if (b + 1 < n_blocks) {
+        MTTS_TRY(layernorm(sb.tmp, C, bl.ln_g, bl.ln_b, nullptr, 0, sb.h1, C, M, C, 1e-5f, 0, 0, st));
+        yin = sb.h1;
+      } else {
+        const bool fin = final_dst && (s == n_stacks - 1);
+        float* out = fin ? final_dst : dst;
+        MTTS_TRY(layernorm(sb.tmp, C, bl.ln_g, bl.ln_b, cur, C, out, C, M, C, 1e-5f, 0, fin ? final_accumulate : 0, st));
+        cur = out;
+      }
+    }
+  }
+  return 0;
+}
+
+static int64_t convnet_ws_floats(const mtts_convnet* n, int B, int T) {
+  return 3 * ((int64_t)B * T * n->hidden + 64);
+}
+
+static int convnet_forward(const mtts_convnet* n, const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb,
+                           int ldy, int B, int T, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  MTTS_REQUIRE(n->k % 2 == 1, "even kernel size");
+  if (B <= 0 || T <= 0) return 0;
+  Arena ar(ws, ws_bytes);
+  const int64_t M = (int64_t)B * T;
+  float* xc = ar.take<float>(M * n->hidden);
+  StackBufs sb;
+  sb.tmp = ar.take<float>(M * n->hidden);
+  sb.h1 = ar.take<float>(M * n->hidden);
+  if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet", ar.off);
+  mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, xc, B, T, n->in_channels, n->hidden, n->k, 1, MTTS_PAD_ZERO);
+  p.ldx = ldx; p.x_batch_stride = x_sb;
+  MTTS_TRY(conv1d(p, st));
+  MTTS_TRY(residual_stack(n->blocks, n->n_stacks, n->n_blocks, n->hidden, n->k, B, T, xc, xc, nullptr, 0, sb, st));
+  mtts_conv_params q = conv_same_params(xc, n->w_last, n->b_last, y, B, T, n->hidden, n->out_channels, n->k, 1, MTTS_PAD_ZERO);
+  q.ldy = ldy; q.y_batch_stride = y_sb;
+  MTTS_TRY(conv1d(q, st));
+  return 0;
+}
+
+static int cnd_mid_len(const mtts_convnet_double* n, int T) {
+  if (n->middle_kind == 0) return (T + n->middle_k - 1) / n->middle_k;
+  return (T + 2 * n->middle_pad - n->middle_k) / n->middle_stride + 1;
+}
+
+static int64_t convnet_double_ws_floats(const mtts_convnet_double* n, int B, int T) {
+  const int Tm = cnd_mid_len(n, T);
+  return 4 * ((int64_t)B * T * n->hidden + 64) + 2 * ((int64_t)B * Tm * n->hidden + 64);
+}
+
+static int convnet_double_forward(const mtts_convnet_double* n, const float* x, int64_t x_sb, int ldx, float* y,
+                                  int64_t y_sb, int ldy, int B, int T, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  MTTS_REQUIRE(n->k % 2 == 1, "even kernel size");
+  if (B <= 0 || T <= 0) return 0;
+  const int H = n->hidden, Tm = cnd_mid_len(n, T);
+  MTTS_REQUIRE(Tm >= 1, "input too short for the middle layer");
+  Arena ar(ws, ws_bytes);
+  const int64_t M = (int64_t)B * T, Mm = (int64_t)B * Tm;
+  float* h0 = ar.take<float>(M * H);
+  float* xc = ar.take<float>(M * H);
+  StackBufs sb;
+  sb.tmp = ar.take<float>(M * H);
+  sb.h1 = ar.take<float>(M * H);
+  float* xm = ar.take<float>(Mm * H);
+  float* acc = ar.take<float>(Mm * H);
+  if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet_double", ar.off);
+  mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, h0, B, T, n->in_channels, H, n->k, 1, MTTS_PAD_ZERO);
+  p.ldx = ldx; p.x_batch_stride = x_sb;
+  MTTS_TRY(conv1d(p, st));
+  const int per = n->n_stacks * n->n_blocks;
+  for (int l = 0; l < n->n_layers; ++l) {
+    const mtts_conv_block* b1 = n->blocks + (int64_t)(l * 2 + 0) * per;
+    const mtts_conv_block* b2 = n->blocks + (int64_t)(l * 2 + 1) * per;
+    // every layer consumes the SAME first_layer output (convnet.py:205-207)
+    MTTS_TRY(residual_stack(b1, n->n_stacks, n->n_blocks, H, n->k, B, T, h0, xc, nullptr, 0, sb, st));
+    if (n->middle_kind == 0) {
+      MTTS_TRY(maxpool_time(xc, (int64_t)T * H, H, xm, (int64_t)Tm * H, H, B, T, H, n->middle_k, st));
+    } else {
+      mtts_conv_params m;
+      memset(&m, 0, sizeof(m));
+      m.x = xc; m.ldx = H; m.x_batch_stride = (int64_t)T * H;
+      m.w = n->w_middle; m.bias = n->b_middle;
+      m.y = xm; m.ldy = H; m.y_batch_stride = (int64_t)Tm * H;
+      m.B = B; m.Tin = T; m.Tout = Tm; m.Cin = H; m.Cout = H;
+      m.k = n->middle_k; m.stride = n->middle_stride; m.dil = 1; m.pad = n->middle_pad; m.out_scale = 1.0f;
+      MTTS_TRY(conv1d(m, st));
+    }
+    MTTS_TRY(residual_stack(b2, n->n_stacks, n->n_blocks, H, n->k, B, Tm, xm, xm, acc, l > 0 ? 1 : 0, sb, st));
+  }
+  mtts_conv_params q = conv_same_params(acc, n->w_last, n->b_last, y, B, Tm, H, n->out_channels, n->k, 1, MTTS_PAD_ZERO);
+  q.ldy = ldy; q.y_batch_stride = y_sb;
+  MTTS_TRY(conv1d(q, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// HiFi-GAN V1 generator (speechbrain HifiganGenerator.inference)
+static int64_t hifigan_ws_floats(const mtts_hifigan* h, int B, int T) {
+  const int64_t Tp = T + 2 * h->inference_padding;
+  int64_t L = Tp, C = h->ch0, big = Tp * C;
+  for (int i = 0; i < h->n_ups; ++i) {
+    L *= h->up_factor[i];
+    C /= 2;
+    if (L * C > big) big = L * C;
+  }
+  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64);
+}
+
+static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int mel_ld, int B, int T, float* wav,
+                           int64_t wav_sb, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  MTTS_REQUIRE(h->n_ups >= 1 && h->n_ups <= 4 && h->n_kernels >= 1, "bad generator config");
+  if (B <= 0 || T <= 0) return 0;
+  const int pad = h->inference_padding;
+  const int Tp = T + 2 * pad;
+  int64_t L = Tp, C = h->ch0, big = (int64_t)Tp * C;
+  for (int i = 0; i < h->n_ups; ++i) {
+    MTTS_REQUIRE(h->up_kernel[i] == 2 * h->up_factor[i], "transposed conv needs kernel == 2 * stride");
+    L *= h->up_factor[i];
+    C /= 2;
+    if (L * C > big) big = L * C;
+  }
+  Arena ar(ws, ws_bytes);
+  float* mp = ar.take<float>((int64_t)B * Tp * h->in_channels);
+  float* bufs[5];
+  for (int i = 0; i < 5; ++i) bufs[i] = ar.take<float>((int64_t)B * big);
+  if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "hifigan", ar.off);
+  // replicate-pad `pad` frames at both ends (HifiganGenerator.inference)
+  MTTS_TRY(copy_strided(mel, mel_sb, mel_ld, 1, mp, (int64_t)Tp * h->in_channels, h->in_channels, 1, B, T,
+                        h->in_channels, pad, st));
+  float* o = bufs[0];     // stage input
+  float* oup = bufs[1];   // after the transposed conv
+  float* xr = bufs[2];    // resblock running value
+  float* xt = bufs[3];    // resblock inner value
+  float* z = bufs[4];     // mean of the resblocks -> next stage input
+  {
+    mtts_conv_params p = conv_same_params(mp, h->w_pre, h->b_pre, o, B, Tp, h->in_channels, h->ch0, 7, 1, MTTS_PAD_REFLECT);
+    MTTS_TRY(conv1d(p, st));
+  }
+  int Lc = Tp, Cc = h->ch0;
+  for (int i = 0; i < h->n_ups; ++i) {
+    const int s = h->up_factor[i], Co = Cc / 2, Lo = Lc * s, pt = (h->up_kernel[i] - s) / 2;
+    {
+      // ConvTranspose1d(k = 2s, stride s, padding (k-s)/2) as a 2-tap conv with s*Co columns:
+      // super-row u in [0, Lc]: out[u*s + r - pt, co] = x[u-1] W[:, co, r+s] + x[u] W[:, co, r]
+      mtts_conv_params p;
+      memset(&p, 0, sizeof(p));
+      p.x = o; p.ldx = Cc; p.x_batch_stride = (int64_t)Lc * Cc;
+      p.w = h->w_up[i]; p.bias = h->b_up[i];
+      p.y = oup; p.ldy = s * Co; p.y_batch_stride = (int64_t)Lo * Co;
+      p.B = B; p.Tin = Lc; p.Tout = Lc + 1; p.Cin = Cc; p.Cout = s * Co;
+      p.k = 2; p.stride = 1; p.dil = 1; p.pad = 1; p.pad_mode = MTTS_PAD_ZERO;
+      p.pre_act = MTTS_ACT_LEAKY; p.pre_slope = 0.1f;
+      p.out_scale = 1.0f;
+      p.out_shift = -(int64_t)pt * Co;
+      p.y_batch_elems = (int64_t)Lo * Co;
+      MTTS_TRY(conv1d(p, st));
+    }
+    for (int j = 0; j < h->n_kernels; ++j) {
+      const mtts_hifigan_resblock& rb = h->resblocks[i * h->n_kernels + j];
+      const float* xcur = oup;
+      for (int m = 0; m < 3; ++m) {
+        mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], xt, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);
+        c1.pre_act = MTTS_ACT_LEAKY; c1.pre_slope = 0.1f;
+        MTTS_TRY(conv1d(c1, st));
+        const bool lastm = (m == 2);
+        mtts_conv_params c2 = conv_same_params(xt, rb.w2[m], rb.b2[m], lastm ? z : xr, B, Lo, Co, Co, rb.k, 1, MTTS_PAD_REFLECT);
+        c2.pre_act = MTTS_ACT_LEAKY; c2.pre_slope = 0.1f;
+        c2.res = xcur; c2.res_batch_stride = (int64_t)Lo * Co; c2.ldr = Co;
+        if (lastm) {
+          c2.out_scale = 1.0f / (float)h->n_kernels;
+          c2.accumulate = (j > 0);
+        }
+        MTTS_TRY(conv1d(c2, st));
+        xcur = xr;
+      }
+    }
+    float* tswap = o; o = z; z = tswap;   // z (mean) becomes the next stage's input
+    Lc = Lo; Cc = Co;
+  }
+  {
+    mtts_conv_params p = conv_same_params(o, h->w_post, h->b_post, wav, B, Lc, Cc, 1, 7, 1, MTTS_PAD_REFLECT);
+    p.pre_act = MTTS_ACT_LEAKY; p.pre_slope = 0.01f;
+    p.post_act = MTTS_ACT_TANH;
+    p.ldy = 1; p.y_batch_stride = wav_sb;
+    MTTS_TRY(conv1d(p, st));
+  }
+  return 0;
+}
+
+}  // namespace mtts
+
+// ==========================================================================================
+// C ABI
+using namespace mtts;
+
+extern "C" {
+
+int mtts_profile_begin(void) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  g_prof_on = true;
+  return 0;
+}
+int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches) {
+  std::lock_guard<std::mutex> lk(g_prof_mu);
+  g_prof_on = false;
+  double ms = 0.0, fl = 0.0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    if (cudaEventSynchronize(r.b) != cudaSuccess || cudaEventElapsedTime(&t, r.a, r.b) != cudaSuccess)
+      return fail(MTTS_ERR_CUDA, "%s: event timing failed", "profile");
+    ms += t;
+    fl += r.flops;
+  }
+  if (gemm_ms) *gemm_ms = ms;
+  if (gemm_flops) *gemm_flops = fl;
+  if (gemm_launches) *gemm_launches = (int64_t)g_prof.size();
+  for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
+  g_prof.clear();
+  return 0;
+}
+
+int64_t mtts_encoder_workspace_bytes(const mtts_encoder* enc, int32_t B, int32_t T) {
+  return encoder_ws_floats(enc, B, T) * 4 + 4096;
+}
+int mtts_encoder_forward_f32(const mtts_encoder* enc, const float* x, float* y, int32_t B, int32_t T, const float* mask,
+                             int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, int32_t last_row_only, void* workspace,
+                             int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(enc && enc->layers && x && y && workspace, "null pointer");
+  Arena ar(workspace, workspace_bytes);
+  return encoder_forward(enc, x, y, B, T, mask, mask_sb, mask_sh, mask_sq, last_row_only, ar, (cudaStream_t)stream);
+}
+
+int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) { return plm_ws_floats(m, B, T) * 4 + 8192; }
+int mtts_plm_infer_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,
+                       int64_t* codes_out, float* logits_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(m && m->enc.layers && workspace, "null pointer");
+  return plm_infer(m, tc_latent, tc_sb, tc_ld, B, T, codes_out, logits_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t mtts_adm_infer_workspace_bytes(const mtts_adm* m, int32_t B, int32_t T) { return adm_ws_floats(m, B, T) * 4 + 8192; }
+int mtts_adm_infer_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,
+                       int32_t* dur_out, float* raw_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(m && m->enc.layers && workspace, "null pointer");
+  return adm_infer(m, tc_latent, tc_sb, tc_ld, B, T, dur_out, raw_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t mtts_convnet_workspace_bytes(const mtts_convnet* n, int32_t B, int32_t T) { return convnet_ws_floats(n, B, T) * 4 + 4096; }
+int mtts_convnet_forward_f32(const mtts_convnet* n, const float* x, int64_t x_sb, int32_t ldx, float* y, int64_t y_sb,
+                             int32_t ldy, int32_t B, int32_t T, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(n && n->blocks && x && y && workspace, "null pointer");
+  return convnet_forward(n, x, x_sb, ldx, y, y_sb, ldy, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int32_t mtts_convnet_double_out_len(const mtts_convnet_double* n, int32_t T) { return cnd_mid_len(n, T); }
+int64_t mtts_convnet_double_workspace_bytes(const mtts_convnet_double* n, int32_t B, int32_t T) {
+  return convnet_double_ws_floats(n, B, T) * 4 + 4096;
+}
+int mtts_convnet_double_forward_f32(const mtts_convnet_double* n, const float* x, int64_t x_sb, int32_t ldx, float* y,
+                                    int64_t y_sb, int32_t ldy, int32_t B, int32_t T, void* workspace,
+                                    int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(n && n->blocks && x && y && workspace, "null pointer");
+  return convnet_double_forward(n, x, x_sb, ldx, y, y_sb, ldy, B, T, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t mtts_hifigan_workspace_bytes(const mtts_hifigan* h, int32_t B, int32_t T) { return hifigan_ws_floats(h, B, T) * 4 + 4096; }
+int mtts_hifigan_forward_f32(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int32_t mel_ld, int32_t B, int32_t T,
+                             float* wav, int64_t wav_sb, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(h && h->resblocks && mel && wav && workspace, "null pointer");
+  return hifigan_forward(h, mel, mel_sb, mel_ld, B, T, wav, wav_sb, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+}  // extern "C"

@@ -1,0 +1,67 @@
+// Internal (C++) entry points shared by the drivers and the C ABI.
+#pragma once
+#include "common.cuh"
+
+namespace mtts {
+int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
+int conv1d(const mtts_conv_params& p, cudaStream_t st);   // engine dispatch (FFMA today)
+int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
+              int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, cudaStream_t st);
+int attention(const mtts_attn_params& p, cudaStream_t st);
+int vq_argmin(const float* x, int ldx, const float* embed, int64_t N, int D, int K, int64_t* idx, cudaStream_t st);
+int vq_gather(const int64_t* idx, int idx_ld, const float* embed, int D, int K, int B, int T_out, int repeat, float* y,
+              int64_t y_sb, int ldy, cudaStream_t st);
+int maxpool_time(const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb, int ldy, int B, int T, int C, int k,
+                 cudaStream_t st);
+int embed_pe(const int64_t* ids, int ids_ld, const float* table, int vocab, int D, const float* pe, float alpha,
+             int pe_offset, int B, int T, float* y, int64_t y_sb, int ldy, cudaStream_t st);
+int add_pe(const float* x, int64_t x_sb, int ldx, const float* pe, float alpha, int B, int T, int D, float* y,
+           int64_t y_sb, int ldy, cudaStream_t st);
+int length_regulate(const float* x, int64_t x_sb, int ldx, const int32_t* dur, int dur_ld, int B, int Tp, int D,
+                    int L_out, float* y, int64_t y_sb, int ldy, int32_t* totals, cudaStream_t st);
+int copy_strided(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc, float* y, int64_t y_sb, int64_t y_st,
+                 int64_t y_sc, int B, int T, int C, int pad_rep, cudaStream_t st);
+int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float* window, const float* fb_w,
+                    const int32_t* fb_off, const int32_t* fb_start, int n_mels, float clamp_min, float* out,
+                    int64_t out_sb, int64_t out_sm, int64_t out_sf, cudaStream_t st);
+// AR-loop helpers
+int plm_build_input(const float* tc, int64_t tc_sb, int tc_ld, int tc_dim, const int64_t* codes, int codes_ld,
+                    const float* emb, int vq_dim, int vocab, const float* pe, float alpha, int B, int S, float* X,
+                    cudaStream_t st);
+int argmax_rows(const float* x, int64_t ldx, int V, int rows, int64_t* out_a, int64_t lda, int64_t* out_b, int64_t ldb,
+                cudaStream_t st);
+int fill_i64(int64_t* p, int64_t stride, int n, int64_t v, cudaStream_t st);
+int fill_f32(float* p, int64_t stride, int n, float v, cudaStream_t st);
+int adm_build_input(const float* tc_emb, int64_t te_sb, int te_ld, int tc_emb_dim, const float* praw, int p_ld,
+                    const float* w_dt, int emb_dim, const float* pe, float alpha, int B, int S, float* X,
+                    cudaStream_t st);
+int adm_readout(const float* xl, int D, const float* w, int B, float* praw, int p_ld, int s_next, cudaStream_t st);
+int adm_finalize(const float* praw, int p_ld, int B, int T, int32_t* dur, float* raw_out, cudaStream_t st);
+
+// convenience: dense linear layer  Y[M,N] = act(X[M,K] W + b) (+ res)
+inline mtts_conv_params linear_params(const float* x, int ldx, const float* w, const float* bias, float* y, int ldy,
+                                      int64_t M, int K, int N) {
+  mtts_conv_params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = ldx; p.x_batch_stride = 0;
+  p.w = w; p.bias = bias;
+  p.y = y; p.ldy = ldy; p.y_batch_stride = 0;
+  p.B = 1; p.Tin = (int32_t)M; p.Tout = (int32_t)M; p.Cin = K; p.Cout = N;
+  p.k = 1; p.stride = 1; p.dil = 1; p.pad = 0; p.pad_mode = MTTS_PAD_ZERO;
+  p.out_scale = 1.0f;
+  return p;
+}
+// "same" stride-1 conv over (B, T, Cin) -> (B, T, Cout), contiguous buffers
+inline mtts_conv_params conv_same_params(const float* x, const float* w, const float* bias, float* y, int B, int T,
+                                         int Cin, int Cout, int k, int dil, int pad_mode) {
+  mtts_conv_params p;
+  memset(&p, 0, sizeof(p));
+  p.x = x; p.ldx = Cin; p.x_batch_stride = (int64_t)T * Cin;
+  p.w = w; p.bias = bias;
+  p.y = y; p.ldy = Cout; p.y_batch_stride = (int64_t)T * Cout;
+  p.B = B; p.Tin = T; p.Tout = T; p.Cin = Cin; p.Cout = Cout;
+  p.k = k; p.stride = 1; p.dil = dil; p.pad = dil * (k - 1) / 2; p.pad_mode = pad_mode;
+  p.out_scale = 1.0f;
+  return p;
+}
+}  // namespace mtts

@@ -1,0 +1,422 @@
+"""MegaG / MegaPLM / MegaADM / Megatts with the reference's surface (models/megatts2.py:30-117,
+120-198, 201-292, 295-375) + a HiFi-GAN vocoder with speechbrain's ``HIFIGAN`` call surface
+(``from_hparams`` / ``decode_batch``; reference call sites models/megatts2.py:321-323, 370-372).
+
+Same class names, ctor kwargs, state_dict keys, ``forward`` / ``infer`` / ``from_hparams`` /
+``from_pretrained`` signatures; all device work in libmegatts2_b200.  Differences, all
+generalisations: ``infer`` accepts B >= 1 (B independent batch-1 runs of the reference, which is
+hard-wired to B = 1 at :170-171, :262-263); ``Megatts.synthesize`` is the tensor-level body of
+``Megatts.forward`` (:353-373) for a batch of utterances."""
+import ctypes as C
+import glob
+
+import torch
+import torch.nn as nn
+import yaml
+
+from .. import _lib as L
+from .. import ops, pack
+from ..modules.convnet import ConvNet
+from ..modules.embedding import SinePositionalEmbedding
+from ..modules.mrte import MRTE, LengthRegulator
+from ..modules.tokenizer import HIFIGAN_HOP_LENGTH, HIFIGAN_SR, extract_mel_spec
+from ..modules.transformer import TransformerEncoder, TransformerEncoderLayer, encoder_plan, run_encoder
+from ..modules.vqpe import VQProsodyEncoder
+from ..utils.utils import instantiate_class
+
+
+def _eval_only(m):
+    if m.training:
+        raise L.MttsError("training-mode forward is outside the synthesis path (call .eval()); "
+                          "backward kernels are a later row (SURVEY.md §8f-4)")
+
+
+class MegaG(nn.Module):
+    def __init__(self, mrte: MRTE, vqpe: VQProsodyEncoder, kernel_size: int = 5, activation: str = 'ReLU',
+                 hidden_size: int = 512, decoder_n_stack: int = 4, decoder_n_block: int = 2):
+        super().__init__()
+        self.mrte = mrte
+        self.vqpe = vqpe
+        self.decoder = ConvNet(
+            in_channels=mrte.hidden_size + vqpe.vq.dimension, out_channels=mrte.mel_bins, hidden_size=hidden_size,
+            n_stacks=decoder_n_stack, n_blocks=decoder_n_block, kernel_size=kernel_size, activation=activation)
+
+    def forward(self, duration_tokens, phone, phone_lens, mel_mrte, mel_vqpe):
+        """(models/megatts2.py:56-74; the reference raises TypeError here at this commit)."""
+        _eval_only(self)
+        zq, commit_loss, vq_loss, _ = self.vqpe(mel_vqpe)
+        x = self.mrte(duration_tokens, phone, phone_lens, mel_mrte)
+        T = min(x.shape[1], zq.shape[1])
+        xin = torch.cat([x[:, :T], zq[:, :T]], dim=-1)
+        return self.decoder.forward_cl(xin), commit_loss, vq_loss
+
+    def s2_latent(self, phone, phone_lens, mel_mrte, mel_vqpe):
+        """(models/megatts2.py:76-84)"""
+        _, _, _, codes = self.vqpe(mel_vqpe)
+        return self.mrte.tc_latent(phone, phone_lens, mel_mrte), codes
+
+    def decode_mel_cl(self, tc_latent_expand: torch.Tensor, p_codes: torch.Tensor) -> torch.Tensor:
+        """Glue of Megatts.forward (models/megatts2.py:361-368): codes -> codebook rows repeated x8,
+        truncated, concatenated with the expanded tc latent, then the ConvNet mel decoder.
+        tc_latent_expand (B,L,512), p_codes (B,T8) int64 -> mel (B,L,80) channels-last."""
+        B, Lm, H = tc_latent_expand.shape
+        D = self.vqpe.vq.dimension
+        x = torch.empty(B, Lm, H + D, dtype=torch.float32, device=tc_latent_expand.device)
+        x[:, :, :H].copy_(tc_latent_expand)                       # layout plumbing (concat)
+        embed = self.vqpe.vq.vq.layers[0]._codebook.embed
+        ops.vq_gather(p_codes, embed, t_out=Lm, repeat=8, out=x[:, :, H:])
+        return self.decoder.forward_cl(x)
+
+    @classmethod
+    def from_hparams(cls, config_path: str) -> "MegaG":
+        with open(config_path, "r") as f:
+            config = yaml.safe_load(f)
+        g_cfg = config['model']['G']
+        g_cfg['init_args']['mrte'] = instantiate_class(args=(), init=g_cfg['init_args']['mrte'])
+        g_cfg['init_args']['vqpe'] = instantiate_class(args=(), init=g_cfg['init_args']['vqpe'])
+        return instantiate_class(args=(), init=g_cfg)
+
+    @classmethod
+    def from_pretrained(cls, ckpt: str, config: str) -> "MegaG":
+        G = cls.from_hparams(config)
+        sd = {k[2:]: v for k, v in torch.load(ckpt, map_location="cpu")['state_dict'].items() if k.startswith('G.')}
+        G.load_state_dict(sd, strict=True)
+        return G
+
+
+class MegaPLM(pack.PlanMixin, nn.Module):
+    def __init__(self, n_layers: int = 12, n_heads: int = 16, vq_dim: int = 512, tc_latent_dim: int = 512,
+                 vq_bins: int = 1024, dropout: float = 0.1):
+        super().__init__()
+        d_model = vq_dim + tc_latent_dim
+        self.plm = TransformerEncoder(
+            TransformerEncoderLayer(dim=d_model, ff_dim=d_model * 4, n_heads=n_heads, dropout=dropout, conv_ff=False),
+            num_layers=n_layers)
+        self.predict_layer = nn.Linear(d_model, vq_bins, bias=False)
+        self.pos = SinePositionalEmbedding(d_model)
+        self.pc_embedding = nn.Embedding(vq_bins + 2, vq_dim)
+        self.vq_bins, self.vq_dim, self.tc_latent_dim = vq_bins, vq_dim, tc_latent_dim
+        self._plan = None
+
+    def _plan_get(self, device, T):
+        sig = pack.signature(list(self.parameters()))
+        if self._plan is None or self._plan.sig != sig or self._plan.pe_rows < T:
+            pl = pack.Plan()
+            pl.sig = sig
+            enc_pl = encoder_plan(self.plm, list(self.plm.layers))
+            pl.hold(enc_pl)
+            s = L.PLM()
+            s.enc = enc_pl.enc
+            s.pc_embedding = pl.p(self.pc_embedding.weight)
+            s.w_predict = pl.p(pack.pack_linear(self.predict_layer.weight))
+            pe = self.pos.table(device, max(T, 4000))
+            pl.pe_rows = pe.shape[0]
+            s.pe = pl.p(pe)
+            s.pe_alpha = self.pos.alpha_host()
+            s.vq_bins, s.vq_dim, s.tc_dim = self.vq_bins, self.vq_dim, self.tc_latent_dim
+            pl.struct = s
+            self._plan = pl
+        return self._plan
+
+    def forward(self, tc_latent: torch.Tensor, p_codes: torch.Tensor, lens: torch.Tensor):
+        """Teacher-forced logits with the causal + padding mask (models/megatts2.py:148-163).
+        Forward only."""
+        _eval_only(self)
+        T = tc_latent.shape[1]
+        dev = tc_latent.device
+        x = torch.empty(tc_latent.shape[0], T, self.tc_latent_dim + self.vq_dim, dtype=torch.float32, device=dev)
+        x[..., :self.tc_latent_dim].copy_(tc_latent)
+        x[..., self.tc_latent_dim:].copy_(ops.embed_pe(p_codes[:, :-1].contiguous(), self.pc_embedding.weight.detach()))
+        x = self.pos(x)
+        h = self.plm(x, lens, causal=True)
+        logits = ops.linear(h, pack.pack_linear(self.predict_layer.weight))
+        return logits, p_codes[:, 1:]
+
+    def infer(self, tc_latent: torch.Tensor, return_logits: bool = False):
+        """Greedy AR decode, BOS = vq_bins, exactly T steps, NON-causal full recompute per step
+        (models/megatts2.py:165-181).  tc_latent (B,T,tc_dim) -> (B,T) int64 [, (B,T,vq_bins) logits]."""
+        _eval_only(self)
+        tc = ops._dev(tc_latent, name="tc_latent")
+        if tc.stride(2) != 1:
+            tc = tc.contiguous()
+        B, T, _ = tc.shape
+        pl = self._plan_get(tc.device, T)
+        lib = L.lib()
+        codes = torch.empty(B, T, dtype=torch.int64, device=tc.device)
+        logits = torch.empty(B, T, self.vq_bins, dtype=torch.float32, device=tc.device) if return_logits else None
+        ws = ops.workspace(lib.mtts_plm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
+        L.check(lib.mtts_plm_infer_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
+                                       codes.data_ptr(), logits.data_ptr() if return_logits else None,
+                                       ws.data_ptr(), ws.numel(), ops._stream()))
+        return (codes, logits) if return_logits else codes
+
+    @classmethod
+    def from_pretrained(cls, ckpt: str, config: str) -> "MegaPLM":
+        with open(config, "r") as f:
+            plm = instantiate_class(args=(), init=yaml.safe_load(f)['model']['plm'])
+        sd = {k[4:]: v for k, v in torch.load(ckpt, map_location="cpu")['state_dict'].items() if k.startswith('plm.')}
+        plm.load_state_dict(sd, strict=True)
+        return plm
+
+
+class MegaADM(pack.PlanMixin, nn.Module):
+    def __init__(self, n_layers: int = 8, n_heads: int = 8, emb_dim: int = 256, tc_latent_dim: int = 512,
+                 tc_emb_dim: int = 256, dropout: float = 0.1, max_duration_token: int = 256):
+        super().__init__()
+        d_model = emb_dim + tc_emb_dim
+        self.adm = TransformerEncoder(
+            TransformerEncoderLayer(dim=d_model, ff_dim=emb_dim * 4, n_heads=n_heads, dropout=dropout, conv_ff=False),
+            num_layers=n_layers)
+        self.dt_linear_emb = nn.Linear(1, emb_dim, bias=False)
+        self.tc_linear_emb = nn.Linear(tc_latent_dim, tc_emb_dim, bias=False)
+        self.pos_emb = SinePositionalEmbedding(d_model)
+        self.predict_layer = nn.Linear(d_model, 1, bias=False)
+        self.max_duration_token = max_duration_token
+        self.emb_dim, self.tc_latent_dim, self.tc_emb_dim = emb_dim, tc_latent_dim, tc_emb_dim
+        self._plan = None
+
+    def _plan_get(self, device, T):
+        sig = pack.signature(list(self.parameters()))
+        if self._plan is None or self._plan.sig != sig or self._plan.pe_rows < T:
+            pl = pack.Plan()
+            pl.sig = sig
+            enc_pl = encoder_plan(self.adm, list(self.adm.layers))
+            pl.hold(enc_pl)
+            s = L.ADM()
+            s.enc = enc_pl.enc
+            s.w_dt = pl.p(self.dt_linear_emb.weight.detach()[:, 0].contiguous())
+            s.w_tc = pl.p(pack.pack_linear(self.tc_linear_emb.weight))
+            s.w_predict = pl.p(self.predict_layer.weight.detach()[0].contiguous())
+            pe = self.pos_emb.table(device, max(T, 4000))
+            pl.pe_rows = pe.shape[0]
+            s.pe = pl.p(pe)
+            s.pe_alpha = self.pos_emb.alpha_host()
+            s.emb_dim, s.tc_dim, s.tc_emb_dim = self.emb_dim, self.tc_latent_dim, self.tc_emb_dim
+            pl.struct = s
+            self._plan = pl
+        return self._plan
+
+    def forward(self, tc_latents: torch.Tensor, duration_tokens: torch.Tensor, lens: torch.Tensor):
+        """Teacher-forced duration regression (models/megatts2.py:233-255).  Forward only."""
+        _eval_only(self)
+        B, T, _ = tc_latents.shape
+        dev = tc_latents.device
+        x = torch.empty(B, T, self.tc_emb_dim + self.emb_dim, dtype=torch.float32, device=dev)
+        x[..., :self.tc_emb_dim].copy_(ops.linear(tc_latents, pack.pack_linear(self.tc_linear_emb.weight)))
+        x[..., self.tc_emb_dim:].copy_(ops.linear(duration_tokens[:, :-1].contiguous().float(),
+                                                  pack.pack_linear(self.dt_linear_emb.weight)))
+        x = self.pos_emb(x)
+        h = self.adm(x, lens, causal=True)
+        pred = ops.linear(h, pack.pack_linear(self.predict_layer.weight))[..., 0]
+        return pred, duration_tokens[:, 1:, 0]
+
+    def infer(self, tc_latents: torch.Tensor, return_raw: bool = False):
+        """AR duration regression, raw float feedback, non-causal full recompute, final
+        (p + 0.5) -> int32 -> clamp(1, 128)  (models/megatts2.py:257-275).
+        tc_latents (B,T,512) -> (B,T,1) int32 [, raw (B,T) fp32]."""
+        _eval_only(self)
+        tc = ops._dev(tc_latents, name="tc_latents")
+        if tc.stride(2) != 1:
+            tc = tc.contiguous()
+        B, T, _ = tc.shape
+        pl = self._plan_get(tc.device, T)
+        lib = L.lib()
+        dur = torch.empty(B, T, dtype=torch.int32, device=tc.device)
+        raw = torch.empty(B, T, dtype=torch.float32, device=tc.device) if return_raw else None
+        ws = ops.workspace(lib.mtts_adm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
+        L.check(lib.mtts_adm_infer_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
+                                       dur.data_ptr(), raw.data_ptr() if return_raw else None,
+                                       ws.data_ptr(), ws.numel(), ops._stream()))
+        dur = dur.unsqueeze(-1)
+        return (dur, raw) if return_raw else dur
+
+    @classmethod
+    def from_pretrained(cls, ckpt: str, config: str) -> "MegaADM":
+        with open(config, "r") as f:
+            adm = instantiate_class(args=(), init=yaml.safe_load(f)['model']['adm'])
+        sd = {k[4:]: v for k, v in torch.load(ckpt, map_location="cpu")['state_dict'].items() if k.startswith('adm.')}
+        adm.load_state_dict(sd, strict=True)
+        return adm
+
+
+# ------------------------------------------------------------------------------------------
+HIFIGAN_V1 = dict(in_channels=80, upsample_initial_channel=512, upsample_factors=(8, 8, 2, 2),
+                  upsample_kernel_sizes=(16, 16, 4, 4), resblock_kernel_sizes=(3, 7, 11),
+                  resblock_dilation_sizes=((1, 3, 5), (1, 3, 5), (1, 3, 5)), inference_padding=5)
+
+
+class HifiganGenerator(pack.PlanMixin, nn.Module):
+    """HiFi-GAN V1 generator, weight-norm already folded (speechbrain HifiganGenerator [published
+    architecture]).  Parameter names: ``conv_pre.{weight,bias}``,
+    ``ups.{i}.{weight,bias}`` (ConvTranspose1d layout (Cin, Cout, k)),
+    ``resblocks.{n}.convs{1,2}.{m}.{weight,bias}``, ``conv_post.{weight,bias}``."""
+
+    def __init__(self, **cfg):
+        super().__init__()
+        c = dict(HIFIGAN_V1)
+        c.update(cfg)
+        self.cfg = c
+        ch = c["upsample_initial_channel"]
+        self.conv_pre = nn.Conv1d(c["in_channels"], ch, 7)
+        self.ups = nn.ModuleList()
+        self.resblocks = nn.ModuleList()
+        for i, (u, k) in enumerate(zip(c["upsample_factors"], c["upsample_kernel_sizes"])):
+            co = ch // (2 ** (i + 1))
+            self.ups.append(nn.ConvTranspose1d(ch // (2 ** i), co, k, stride=u, padding=(k - u) // 2))
+            for j, rk in enumerate(c["resblock_kernel_sizes"]):
+                rb = nn.Module()
+                rb.convs1 = nn.ModuleList([nn.Conv1d(co, co, rk, dilation=d) for d in c["resblock_dilation_sizes"][j]])
+                rb.convs2 = nn.ModuleList([nn.Conv1d(co, co, rk) for _ in c["resblock_dilation_sizes"][j]])
+                self.resblocks.append(rb)
+        self.conv_post = nn.Conv1d(ch // (2 ** len(c["upsample_factors"])), 1, 7)
+        self._plan = None
+
+    def _plan_get(self):
+        sig = pack.signature(list(self.parameters()))
+        if self._plan is None or self._plan.sig != sig:
+            c = self.cfg
+            pl = pack.Plan()
+            pl.sig = sig
+            s = L.Hifigan()
+            s.in_channels, s.ch0 = c["in_channels"], c["upsample_initial_channel"]
+            s.n_ups, s.n_kernels = len(c["upsample_factors"]), len(c["resblock_kernel_sizes"])
+            s.inference_padding = c["inference_padding"]
+            s.w_pre, s.b_pre = pl.p(pack.pack_conv(self.conv_pre.weight)), pl.p(self.conv_pre.bias)
+            for i, (u, k) in enumerate(zip(c["upsample_factors"], c["upsample_kernel_sizes"])):
+                s.up_factor[i], s.up_kernel[i] = u, k
+                wp, bp = pack.pack_conv_transpose(self.ups[i].weight, self.ups[i].bias, u)
+                s.w_up[i], s.b_up[i] = pl.p(wp), pl.p(bp)
+            arr = (L.HifiganResblock * len(self.resblocks))()
+            for n, rb in enumerate(self.resblocks):
+                j = n % s.n_kernels
+                arr[n].k = c["resblock_kernel_sizes"][j]
+                assert len(rb.convs1) == 3
+                for m in range(3):
+                    arr[n].dil[m] = c["resblock_dilation_sizes"][j][m]
+                    arr[n].w1[m], arr[n].b1[m] = pl.p(pack.pack_conv(rb.convs1[m].weight)), pl.p(rb.convs1[m].bias)
+                    arr[n].w2[m], arr[n].b2[m] = pl.p(pack.pack_conv(rb.convs2[m].weight)), pl.p(rb.convs2[m].bias)
+            pl.hold(arr)
+            s.resblocks = C.cast(arr, C.POINTER(L.HifiganResblock))
+            s.w_post, s.b_post = pl.p(pack.pack_conv(self.conv_post.weight)), pl.p(self.conv_post.bias)
+            pl.struct = s
+            self._plan = pl
+        return self._plan
+
+    def out_len(self, T):
+        n = T + 2 * self.cfg["inference_padding"]
+        for u in self.cfg["upsample_factors"]:
+            n *= u
+        return n
+
+    def inference_cl(self, mel_cl: torch.Tensor) -> torch.Tensor:
+        """mel (B, T, 80) channels-last -> wav (B, 1, 256*(T+10))."""
+        mel = ops._dev(mel_cl, name="mel")
+        if mel.stride(2) != 1:
+            mel = mel.contiguous()
+        B, T, _ = mel.shape
+        pl = self._plan_get()
+        lib = L.lib()
+        wav = torch.empty(B, 1, self.out_len(T), dtype=torch.float32, device=mel.device)
+        ws = ops.workspace(lib.mtts_hifigan_workspace_bytes(C.byref(pl.struct), B, T), mel.device)
+        L.check(lib.mtts_hifigan_forward_f32(C.byref(pl.struct), mel.data_ptr(), mel.stride(0), mel.stride(1), B, T,
+                                             wav.data_ptr(), wav.stride(0), ws.data_ptr(), ws.numel(), ops._stream()))
+        return wav
+
+    def inference(self, c: torch.Tensor, padding: bool = True) -> torch.Tensor:
+        """c (B, 80, T) -> (B, 1, 256*(T+10))"""
+        assert padding, "inference without padding is not on the synthesis path"
+        return self.inference_cl(ops.to_channels_last(c))
+
+
+class HIFIGAN(nn.Module):
+    """speechbrain.pretrained.HIFIGAN call surface used by the reference
+    (models/megatts2.py:321-323, 370-372): ``from_hparams(source=...)``, ``eval()``,
+    ``decode_batch(mel (B,80,T)) -> (B,1,samples)``.  There is no network here, so
+    ``from_hparams`` takes an explicit ``state_dict`` (weight-norm folded) or leaves the
+    generator at its constructor init."""
+
+    def __init__(self, generator: HifiganGenerator = None):
+        super().__init__()
+        self.generator = generator if generator is not None else HifiganGenerator()
+
+    @classmethod
+    def from_hparams(cls, source=None, state_dict=None, device=None, **kw):
+        m = cls()
+        if state_dict is not None:
+            m.generator.load_state_dict(state_dict, strict=True)
+        if device is not None:
+            m = m.to(device)
+        return m.eval()
+
+    def decode_batch(self, spectrogram: torch.Tensor, mel_lens=None, hop_len=None) -> torch.Tensor:
+        dev = next(self.generator.parameters()).device
+        return self.generator.inference(spectrogram.to(dev))
+
+    def decode_batch_cl(self, mel_cl: torch.Tensor) -> torch.Tensor:
+        return self.generator.inference_cl(mel_cl)
+
+
+class Megatts(nn.Module):
+    """Inference orchestrator (models/megatts2.py:295-375).  ``synthesize`` is the tensor-level
+    body of the reference's ``forward`` for a batch; ``forward(wavs_dir, text)`` keeps the
+    reference signature and needs the reference's host-side text/audio front end
+    (librosa, G2P, symbol table - out of the hot path) to be importable."""
+
+    def __init__(self, g_ckpt: str = None, g_config: str = None, plm_ckpt: str = None, plm_config: str = None,
+                 adm_ckpt: str = None, adm_config: str = None, symbol_table: str = None, *,
+                 generator: MegaG = None, plm: MegaPLM = None, adm: MegaADM = None, hifi_gan: HIFIGAN = None,
+                 device="cuda"):
+        super().__init__()
+        self.generator = generator if generator is not None else MegaG.from_pretrained(g_ckpt, g_config)
+        self.plm = plm if plm is not None else MegaPLM.from_pretrained(plm_ckpt, plm_config)
+        self.adm = adm if adm is not None else MegaADM.from_pretrained(adm_ckpt, adm_config)
+        self.lr = LengthRegulator(HIFIGAN_HOP_LENGTH, 16000, (HIFIGAN_HOP_LENGTH / HIFIGAN_SR * 1000))
+        self.hifi_gan = hifi_gan if hifi_gan is not None else HIFIGAN.from_hparams(
+            source="speechbrain/tts-hifigan-libritts-16kHz")
+        self.symbol_table = symbol_table
+        self.to(device)
+        self.eval()
+
+    @torch.no_grad()
+    def synthesize(self, phone_tokens: torch.Tensor, mels: torch.Tensor, forced_durations: torch.Tensor = None,
+                   return_intermediates: bool = False):
+        """phone_tokens (B,Tp) int64, mels (B,Tm,80) prompt mel (frames-major) -> wav (B,1,256*(sum d + 10)).
+        Steps = models/megatts2.py:354-370.  ``forced_durations`` (B,Tp) int32 replaces the ADM output
+        for shape control (the ADM still runs)."""
+        tc_latent = self.generator.mrte.tc_latent(phone_tokens, mels)
+        dt = self.adm.infer(tc_latent)[..., 0]
+        d_used = dt if forced_durations is None else forced_durations.to(dt.device, torch.int32)
+        tc_expand = self.lr(tc_latent, d_used)                    # one host sync for the output length
+        tc8 = ops.maxpool_time(tc_expand, 8)
+        p_codes = self.plm.infer(tc8)
+        mel = self.generator.decode_mel_cl(tc_expand, p_codes)    # (B, L, 80) channels-last
+        wav = self.hifi_gan.decode_batch_cl(mel)
+        if return_intermediates:
+            return dict(tc_latent=tc_latent, dt=dt, tc_latent_expand=tc_expand, tc8=tc8, p_codes=p_codes,
+                        mel=mel, wav=wav)
+        return wav
+
+    def forward(self, wavs_dir: str, text: str):
+        """Reference signature (models/megatts2.py:325-375): prompt wavs + text -> writes test.wav."""
+        try:
+            import librosa
+            import torchaudio
+            from modules.tokenizer import TextTokenizer          # the reference's host-side G2P
+            from modules.datamodule import TokensCollector
+        except Exception as e:   # pragma: no cover - host front end is outside the hot path
+            raise L.MttsError("Megatts.forward needs the reference's host-side text/audio front end "
+                              f"(librosa, G2P, TokensCollector): {e}; use synthesize() with tensors") from e
+        dev = next(self.parameters()).device
+        mels, mels_prompt = [], None
+        for wav in glob.glob(f'{wavs_dir}/*.wav'):
+            y = torch.from_numpy(librosa.util.normalize(librosa.load(wav, sr=HIFIGAN_SR)[0])).to(dev)
+            m = extract_mel_spec(y.unsqueeze(0), frames_major=True)[0]
+            mels.append(m)
+            mels_prompt = m if mels_prompt is None else mels_prompt
+        mels = torch.cat(mels, 0).unsqueeze(0)
+        tt, ttc = TextTokenizer(), TokensCollector(self.symbol_table)
+        phone_tokens = ttc.phone2token(tt.tokenize_lty(tt.tokenize(text))).unsqueeze(0).to(dev)
+        audio = self.synthesize(phone_tokens, mels)
+        audio_prompt = self.hifi_gan.decode_batch_cl(mels_prompt.unsqueeze(0))
+        audio = torch.cat([audio_prompt, audio], dim=-1)
+        torchaudio.save('test.wav', audio[0].cpu(), HIFIGAN_SR)

@@ -1,0 +1,73 @@
+"""Mel front end with the reference's surface: ``extract_mel_spec`` and the HIFIGAN_*
+constants of modules/tokenizer.py:19-24, 107-125 (speechbrain ``mel_spectogram`` ->
+torchaudio ``MelSpectrogram`` -> log(clamp(., 1e-5))).  The G2P /
+lhotse pieces of that file are host string processing and stay the reference's.
+Device work: libmegatts2_b200 ``mtts_mel_spectrogram_f32``."""
+import math
+
+import numpy as np
+import torch
+
+from .. import ops
+
+HIFIGAN_SR = 16000
+HIFIGAN_HOP_LENGTH = 256
+HIFIGAN_WIN_LENGTH = 1024
+HIFIGAN_MEL_CHANNELS = 80
+HIFIGAN_NFFT = 1024
+HIFIGAN_MAX_FREQ = 8000
+
+
+def slaney_mel_filterbank(n_freqs=HIFIGAN_NFFT // 2 + 1, f_min=0.0, f_max=float(HIFIGAN_MAX_FREQ),
+                          n_mels=HIFIGAN_MEL_CHANNELS, sample_rate=HIFIGAN_SR):
+    """(n_freqs, n_mels) fp32 triangular filterbank on the Slaney mel scale with Slaney
+    (area) normalisation - what mel_scale="slaney", norm="slaney" request at tokenizer.py:121-122.
+    Built in float64 on the host: mel(f) = 3f/200 below 1 kHz, 15 + 27 ln(f/1000)/ln 6.4 above."""
+    knee_hz, knee_mel, slope, step = 1000.0, 15.0, 3.0 / 200.0, math.log(6.4) / 27.0
+    to_mel = lambda f: f * slope if f < knee_hz else knee_mel + math.log(f / knee_hz) / step  # noqa: E731
+    mel_pts = np.linspace(to_mel(f_min), to_mel(f_max), n_mels + 2)
+    hz_pts = np.where(mel_pts < knee_mel, mel_pts / slope, knee_hz * np.exp(step * (mel_pts - knee_mel)))
+    bins = np.linspace(0.0, sample_rate // 2, n_freqs)[:, None]
+    left, centre, right = hz_pts[None, :-2], hz_pts[None, 1:-1], hz_pts[None, 2:]
+    tri = np.maximum(np.minimum((bins - left) / (centre - left), (right - bins) / (right - centre)), 0.0)
+    return (tri * (2.0 / (right - left))).astype(np.float32)
+
+
+class _MelTables:
+    """Window + banded filterbank tables, built once per device."""
+    _cache = {}
+
+    @classmethod
+    def get(cls, device):
+        key = (device.type, device.index)
+        t = cls._cache.get(key)
+        if t is None:
+            fb = slaney_mel_filterbank()                      # (513, 80)
+            offs, starts, weights = [0], [], []
+            for m in range(fb.shape[1]):
+                nz = np.nonzero(fb[:, m])[0]
+                lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 0)
+                starts.append(lo)
+                weights.append(fb[lo:hi, m])
+                offs.append(offs[-1] + (hi - lo))
+            # the exact fp32 table torchaudio's MelSpectrogram uses (window_fn=torch.hann_window, periodic)
+            window = torch.hann_window(HIFIGAN_WIN_LENGTH, periodic=True, dtype=torch.float32)
+            t = dict(
+                window=window.to(device),
+                fb_w=torch.from_numpy(np.concatenate(weights)).to(device),
+                fb_off=torch.tensor(offs, dtype=torch.int32, device=device),
+                fb_start=torch.tensor(starts, dtype=torch.int32, device=device),
+            )
+            cls._cache[key] = t
+        return t
+
+
+def extract_mel_spec(samples: torch.Tensor, frames_major: bool = False) -> torch.Tensor:
+    """samples (L,) or (B, L) fp32 CUDA -> (80, F) / (B, 80, F), F = 1 + L // 256
+    (frames_major=True returns (B, F, 80), the layout Megatts.forward transposes to)."""
+    squeeze = samples.dim() == 1
+    x = samples.unsqueeze(0) if squeeze else samples
+    t = _MelTables.get(x.device)
+    out = ops.mel_spectrogram(x, t["window"], t["fb_w"], t["fb_off"], t["fb_start"], HIFIGAN_MEL_CHANNELS, 1e-5,
+                              frames_major=frames_major)
+    return out[0] if squeeze else out

@@ -74,7 +74,7 @@ def mel_spectrogram(wav, n_fft=1024, hop=256, n_mels=80, f_min=0.0, f_max=8000.0
     SURVEY.md Appendix B."""
     lead = wav.shape[:-1]
     x = wav.reshape(-1, wav.shape[-1]).to(torch.float32)
-    win = torch.from_numpy(hann_periodic(n_fft))
+    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)   # torchaudio's window_fn default
     spec = torch.stft(x, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win, center=True,
                       pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
     mag = spec.abs()                                        # (N, 513, F)   power = 1

@@ -1,0 +1,175 @@
+"""CPU: the C-ABI library loads and exports every symbol include/megatts2_b200.h declares;
+host-side logic (weight packing, masks, filterbank tables, module surface / state_dict keys,
+loud failure without CUDA).  No compute call is made (there is no GPU here)."""
+import ctypes
+import json
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from conftest import GOLDEN, ROOT
+
+
+def _header_symbols():
+    txt = open(os.path.join(ROOT, "include", "megatts2_b200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(mtts_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    from megatts2_b200 import _lib as L
+    lib = L.lib()
+    syms = _header_symbols()
+    assert len(syms) == 29
+    raw = ctypes.CDLL(L.LIB_PATH)
+    for s in syms:
+        assert hasattr(raw, s), f"missing export {s}"
+        assert s in L.SIGNATURES, f"{s} has no ctypes signature"
+    assert set(L.SIGNATURES) == set(syms)
+    assert lib.mtts_abi_version() == 1
+    assert lib.mtts_launch_count() == 0
+
+
+def test_error_reporting_without_gpu():
+    from megatts2_b200 import _lib as L
+    lib = L.lib()
+    assert lib.mtts_conv1d_f32(None, None) == -1
+    assert b"null params" in lib.mtts_last_error()
+    with pytest.raises(L.MttsError):
+        L.check(lib.mtts_attention_f32(None, None))
+
+
+def test_no_cpu_fallback():
+    from megatts2_b200 import _lib as L
+    from megatts2_b200 import ops
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    with pytest.raises(L.MttsError, match="CUDA"):
+        ops.layernorm(torch.zeros(2, 8), torch.ones(8), torch.zeros(8))
+    if not torch.cuda.is_available():
+        with pytest.raises(Exception):
+            extract_mel_spec(torch.zeros(4000))
+
+
+def test_product_never_imports_oracle():
+    bad = []
+    for dp, _, fns in os.walk(os.path.join(ROOT, "megatts2_b200")):
+        for fn in fns:
+            if fn.endswith((".py", ".cu", ".cuh", ".h")):
+                if re.search(r"^\s*(from|import)\s+oracle|oracle/", open(os.path.join(dp, fn)).read(), flags=re.M):
+                    bad.append(fn)
+    assert not bad, bad
+
+
+# ------------------------------------------------------------------ packing (emulated tap-GEMM)
+def _tapconv_emulate(x, wp, bias, k, stride, dil, pad, t_out, ldy_cols, out_shift, y_elems):
+    """Python restatement of the kernel contract in include/megatts2_b200.h (zero padding)."""
+    B, Tin, Cin = x.shape
+    Cout = wp.shape[2]
+    y = torch.zeros(B, y_elems)
+    for b in range(B):
+        for t in range(t_out):
+            acc = torch.zeros(Cout) if bias is None else bias.clone()
+            for j in range(k):
+                ti = t * stride + j * dil - pad
+                if 0 <= ti < Tin:
+                    acc = acc + x[b, ti] @ wp[j]
+            for n in range(Cout):
+                flat = t * ldy_cols + n + out_shift
+                if 0 <= flat < y_elems:
+                    y[b, flat] = acc[n]
+    return y
+
+
+def test_pack_conv_and_linear_layouts():
+    from megatts2_b200 import pack
+    g = torch.Generator().manual_seed(0)
+    w = torch.randn(6, 4, 3, generator=g)
+    b = torch.randn(6, generator=g)
+    x = torch.randn(2, 9, 4, generator=g)
+    ref = F.conv1d(x.transpose(1, 2), w, b, padding=1).transpose(1, 2)
+    y = _tapconv_emulate(x, pack.pack_conv(w), b, 3, 1, 1, 1, 9, 6, 0, 9 * 6).view(2, 9, 6)
+    assert torch.allclose(y, ref, atol=1e-5)
+    wl = torch.randn(5, 4, generator=g)
+    yl = _tapconv_emulate(x, pack.pack_linear(wl), None, 1, 1, 1, 0, 9, 5, 0, 45).view(2, 9, 5)
+    assert torch.allclose(yl, F.linear(x, wl), atol=1e-5)
+    # strided conv (MRTE middle layer geometry: k = s + 1, pad = s // 2)
+    ws = torch.randn(3, 4, 5, generator=g)
+    refs = F.conv1d(x.transpose(1, 2), ws, None, stride=4, padding=2).transpose(1, 2)
+    ys = _tapconv_emulate(x, pack.pack_conv(ws), None, 5, 4, 1, 2, refs.shape[1], 3, 0, refs.shape[1] * 3)
+    assert torch.allclose(ys.view(refs.shape), refs, atol=1e-5)
+
+
+@pytest.mark.parametrize("s", [2, 8])
+def test_pack_conv_transpose_is_two_tap_conv(s):
+    """ConvTranspose1d(k=2s, stride s, pad s/2) == the 2-tap / s*Cout-column form the driver launches."""
+    from megatts2_b200 import pack
+    g = torch.Generator().manual_seed(1)
+    cin, cout, T = 3, 2, 5
+    w = torch.randn(cin, cout, 2 * s, generator=g)
+    b = torch.randn(cout, generator=g)
+    x = torch.randn(2, T, cin, generator=g)
+    ref = F.conv_transpose1d(x.transpose(1, 2), w, b, stride=s, padding=s // 2).transpose(1, 2)   # (B, sT, cout)
+    assert ref.shape[1] == s * T
+    wp, bp = pack.pack_conv_transpose(w, b, s)
+    y = _tapconv_emulate(x, wp, bp, 2, 1, 1, 1, T + 1, s * cout, -(s // 2) * cout, s * T * cout)
+    assert torch.allclose(y.view(2, s * T, cout), ref, atol=1e-5)
+
+
+def test_attn_mask_matches_oracle():
+    from megatts2_b200.utils.utils import make_attn_mask
+    from oracle import ref_megatts2 as R
+    lens = torch.tensor([5, 5], dtype=torch.int32)
+    assert torch.equal(make_attn_mask(lens, 3, True), R.attn_mask(lens, 3, True))
+    lens = torch.tensor([3, 5], dtype=torch.int32)
+    assert torch.equal(make_attn_mask(lens, 2, False), R.attn_mask(lens, 2, False))
+
+
+def test_mel_tables_match_oracle():
+    from megatts2_b200.modules import tokenizer as tk
+    from oracle import ref_megatts2 as R
+    fb = torch.from_numpy(tk.slaney_mel_filterbank())
+    assert (fb - R.slaney_fbanks()).abs().max() < 1e-7
+    t = tk._MelTables.get(torch.device("cpu"))
+    assert t["fb_w"].numel() == 1001 and t["fb_off"][-1] == 1001
+    # banded form reproduces the dense matrix
+    dense = torch.zeros(513, 80)
+    for m in range(80):
+        o0, o1, s0 = int(t["fb_off"][m]), int(t["fb_off"][m + 1]), int(t["fb_start"][m])
+        dense[s0:s0 + (o1 - o0), m] = t["fb_w"][o0:o1]
+    assert torch.equal(dense, fb)
+    assert torch.equal(t["window"], torch.hann_window(1024))
+
+
+def test_module_surface_and_state_dict_keys():
+    """Drop-in contract: constructing from the plugin YAMLs gives the reference's state_dict layout."""
+    from megatts2_b200.models.megatts2 import MegaG
+    from megatts2_b200.utils.utils import instantiate_class
+    import yaml
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as f:
+        ref = json.load(f)
+    cfg = os.path.join(ROOT, "configs")
+    with torch.device("meta"):
+        G = MegaG.from_hparams(os.path.join(cfg, "config_gan.yaml"))
+        plm = instantiate_class((), yaml.safe_load(open(os.path.join(cfg, "config_plm.yaml")))["model"]["plm"])
+        adm = instantiate_class((), yaml.safe_load(open(os.path.join(cfg, "config_adm.yaml")))["model"]["adm"])
+    for name, mod in (("G", G), ("plm", plm), ("adm", adm)):
+        sd = mod.state_dict()
+        assert list(sd.keys()) == list(ref[name].keys()), name
+        assert {k: list(v.shape) for k, v in sd.items()} == ref[name], name
+    # the shared strided conv is ONE module under six names (modules/mrte.py:101-118)
+    assert G.mrte.mel_encoder.layers[3].middle_layer is G.mrte.mel_encoder_middle_layer
+    assert G.vqpe.vq.dimension == 256 and G.mrte.hidden_size == 512 and G.mrte.mel_bins == 80
+
+
+def test_hifigan_state_dict_matches_oracle_spec():
+    from megatts2_b200.models.megatts2 import HifiganGenerator
+    from oracle import weights
+    with torch.device("meta"):
+        gen = HifiganGenerator()
+    sd = gen.state_dict()
+    spec = weights.hifigan_spec()
+    assert set(sd.keys()) == set(spec.keys())
+    assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)

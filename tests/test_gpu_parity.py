@@ -1,0 +1,451 @@
+"""GPU parity: the CUDA path (through the C ABI) against (1) the golden fixtures written by the
+REAL reference, (2) the CPU oracle on seeded inputs, (3) size-independent properties.
+
+Bars: integer outputs (VQ codes, PLM ids, durations, gather indices) bit-exact; floating
+point within the tolerance written next to each check (fp32 vs fp32 with different
+summation order; the noise floors are in SURVEY.md §7.2)."""
+import math
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers
+from oracle import ref_megatts2 as R
+from oracle import weights
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gen(seed):
+    g = torch.Generator()
+    g.manual_seed(seed)
+    return g
+
+
+def maxerr(a, b):
+    return (a.detach().float().cpu() - b.detach().float().cpu()).abs().max().item()
+
+
+@pytest.fixture(scope="module")
+def G(weights_cpu):
+    return helpers.build_g(weights_cpu("g"), DEV)
+
+
+@pytest.fixture(scope="module")
+def PLM(weights_cpu):
+    return helpers.build_plm(weights_cpu("plm"), DEV)
+
+
+@pytest.fixture(scope="module")
+def ADM(weights_cpu):
+    return helpers.build_adm(weights_cpu("adm"), DEV)
+
+
+@pytest.fixture(scope="module")
+def HIFI(weights_cpu):
+    return helpers.build_hifigan(weights_cpu("hifigan"), DEV)
+
+
+# ------------------------------------------------------------------------------ tap-GEMM
+CONV_CASES = [
+    # B, T, Cin, Cout, k, stride, dil, pad_mode, pre, post, res, acc, scale
+    dict(B=1, T=300, Cin=1024, Cout=4096, k=1),                                  # 64x64 tiles
+    dict(B=4, T=700, Cin=1024, Cout=1024, k=1, res=True),                        # 128x128 tiles
+    dict(B=2, T=125, Cin=20, Cout=384, k=5),                                     # Cin % 16 != 0
+    dict(B=2, T=131, Cin=512, Cout=80, k=5),                                     # Cout = 80
+    dict(B=3, T=257, Cin=32, Cout=1, k=7, pad_mode=1, pre=2, post=3),            # conv_post: reflect, leaky, tanh
+    dict(B=2, T=500, Cin=512, Cout=512, k=17, stride=16, pad=8),                 # MRTE strided conv
+    dict(B=2, T=200, Cin=64, Cout=64, k=11, dil=5, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),
+    dict(B=2, T=333, Cin=32, Cout=32, k=3, dil=3, pad_mode=1, pre=2),            # 128x32 tiles
+    dict(B=1, T=97, Cin=7, Cout=5, k=3),                                         # scalar loads both sides
+    dict(B=5, T=1, Cin=768, Cout=768, k=1, res=True),                            # last-row GEMM shape
+    dict(B=2, T=64, Cin=80, Cout=512, k=7, pad_mode=1),                          # conv_pre
+    dict(B=2, T=50, Cin=16, Cout=24, k=5, pad_mode=2),                           # replicate padding
+]
+
+
+@pytest.mark.parametrize("case", CONV_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv1d_vs_torch(case):
+    from megatts2_b200 import ops, pack
+    c = dict(stride=1, dil=1, pad_mode=0, pre=0, post=0, res=False, acc=False, scale=1.0)
+    c.update(case)
+    k, dil = c["k"], c["dil"]
+    pad = c.get("pad", dil * (k - 1) // 2)
+    g = gen(hash(str(case)) % 10000)
+    x = torch.randn(c["B"], c["T"], c["Cin"], generator=g)
+    w = torch.randn(c["Cout"], c["Cin"], k, generator=g) / math.sqrt(c["Cin"] * k)
+    b = torch.randn(c["Cout"], generator=g)
+    xin = x
+    if c["pre"] == 2:
+        xin = F.leaky_relu(x, 0.1)
+    elif c["pre"] == 1:
+        xin = F.relu(x)
+    xt = xin.transpose(1, 2)
+    if pad > 0 and c["pad_mode"] != 0:
+        xt = F.pad(xt, (pad, pad), mode={1: "reflect", 2: "replicate"}[c["pad_mode"]])
+        ref = F.conv1d(xt.double(), w.double(), b.double(), stride=c["stride"], dilation=dil)
+    else:
+        ref = F.conv1d(xt.double(), w.double(), b.double(), stride=c["stride"], dilation=dil, padding=pad)
+    ref = ref.transpose(1, 2)
+    if c["post"] == 3:
+        ref = torch.tanh(ref)
+    res = torch.randn(ref.shape, generator=g) if c["res"] else None
+    y0 = torch.randn(ref.shape, generator=g) if c["acc"] else None
+    if res is not None:
+        ref = ref + res.double()
+    ref = ref * c["scale"]
+    if y0 is not None:
+        ref = ref + y0.double()
+    out = y0.clone().to(DEV) if y0 is not None else None
+    y = ops.conv1d(x.to(DEV), pack.pack_conv(w).to(DEV), b.to(DEV), k=k, stride=c["stride"], dil=dil, pad=pad,
+                   pad_mode=c["pad_mode"], pre_act=c["pre"], pre_slope=0.1, post_act=c["post"],
+                   res=res.to(DEV) if res is not None else None, out=out, out_scale=c["scale"], accumulate=c["acc"])
+    assert y.shape == ref.shape
+    # fp32 accumulation over K = Cin*k terms of O(1/sqrt(K)) products: error ~ 1e-6 * sqrt(K)
+    assert maxerr(y, ref) < 2e-5 * max(1.0, ref.abs().max().item())
+
+
+def test_conv1d_in_lens_and_strided_views():
+    from megatts2_b200 import ops, pack
+    g = gen(7)
+    x = torch.randn(3, 40, 48, generator=g)
+    w = torch.randn(16, 24, 5, generator=g) * 0.1
+    lens = torch.tensor([40, 17, 29], dtype=torch.int32)
+    xs = x[..., 8:32]                       # channel slice: ldx = 48, Cin = 24
+    ref = []
+    for b in range(3):
+        xb = xs[b:b + 1, :lens[b]].transpose(1, 2)
+        ref.append(F.conv1d(xb, w, None, padding=2).transpose(1, 2))
+    y = ops.conv1d(xs.to(DEV), pack.pack_conv(w).to(DEV), None, k=5, pad=2, in_lens=lens.to(DEV))
+    for b in range(3):
+        assert maxerr(y[b, :lens[b]], ref[b][0]) < 1e-5
+
+
+def test_conv_transpose_form_vs_torch():
+    from megatts2_b200 import _lib as L
+    from megatts2_b200 import ops, pack
+    import ctypes as C
+    g = gen(11)
+    for (cin, cout, s, T, B) in [(512, 256, 8, 37, 2), (128, 64, 2, 301, 3)]:
+        x = torch.randn(B, T, cin, generator=g)
+        w = torch.randn(cin, cout, 2 * s, generator=g) / math.sqrt(cin * 2)
+        b = torch.randn(cout, generator=g)
+        ref = F.conv_transpose1d(F.leaky_relu(x, 0.1).transpose(1, 2), w, b, stride=s, padding=s // 2).transpose(1, 2)
+        wp, bp = pack.pack_conv_transpose(w, b, s)
+        xd, wp, bp = x.to(DEV), wp.to(DEV), bp.to(DEV)
+        y = torch.empty(B, s * T, cout, device=DEV)
+        p = L.ConvParams()
+        p.x, p.x_batch_stride, p.ldx = xd.data_ptr(), T * cin, cin
+        p.w, p.bias = wp.data_ptr(), bp.data_ptr()
+        p.y, p.y_batch_stride, p.ldy = y.data_ptr(), s * T * cout, s * cout
+        p.B, p.Tin, p.Tout, p.Cin, p.Cout = B, T, T + 1, cin, s * cout
+        p.k, p.stride, p.dil, p.pad, p.pad_mode = 2, 1, 1, 1, 0
+        p.pre_act, p.pre_slope, p.out_scale = L.ACT_LEAKY, 0.1, 1.0
+        p.out_shift, p.y_batch_elems = -(s // 2) * cout, s * T * cout
+        L.check(L.lib().mtts_conv1d_f32(C.byref(p), ops._stream()))
+        assert maxerr(y, ref) < 2e-5
+
+
+def test_conv_linearity_property_full_size():
+    """size-independent property at a BASELINE-size GEMM: f(a x1 + x2) == a f(x1) + f(x2) (no bias)."""
+    from megatts2_b200 import ops
+    g = torch.Generator(device=DEV)
+    g.manual_seed(3)
+    x1 = torch.randn(1, 4096, 1024, device=DEV, generator=g)
+    x2 = torch.randn(1, 4096, 1024, device=DEV, generator=g)
+    w = torch.randn(1, 1024, 4096, device=DEV, generator=g) / 32
+    lhs = ops.conv1d(2.0 * x1 + x2, w, None, k=1)
+    rhs = 2.0 * ops.conv1d(x1, w, None, k=1) + ops.conv1d(x2, w, None, k=1)
+    assert (lhs - rhs).abs().max().item() < 5e-5
+    # and against cuBLAS-free fp64 on a row sample
+    rows = torch.tensor([0, 1, 777, 4095], device=DEV)
+    ref = (x1[0, rows].double() @ w[0].double())
+    assert (ops.conv1d(x1, w, None, k=1)[0, rows].double() - ref).abs().max().item() < 5e-5
+
+
+# ------------------------------------------------------------------------------ LN / attention
+@pytest.mark.parametrize("C_", [384, 512, 768, 1024, 100])
+def test_layernorm(C_):
+    from megatts2_b200 import ops
+    g = gen(C_)
+    x = torch.randn(37, C_, generator=g) * 3 + 1
+    ga, be = torch.randn(C_, generator=g), torch.randn(C_, generator=g)
+    res, y0 = torch.randn(37, C_, generator=g), torch.randn(37, C_, generator=g)
+    ref = F.layer_norm(x.double(), (C_,), ga.double(), be.double(), 1e-5)
+    y = ops.layernorm(x.to(DEV), ga.to(DEV), be.to(DEV))
+    assert maxerr(y, ref) < 1e-5
+    ref2 = F.relu(ref) + res.double() + y0.double()
+    y2 = ops.layernorm(x.to(DEV), ga.to(DEV), be.to(DEV), res=res.to(DEV), out=y0.clone().to(DEV), post_act=1,
+                       accumulate=True)
+    assert maxerr(y2, ref2) < 1e-5
+    xi = x.clone().to(DEV)                  # in place
+    ops.layernorm(xi, ga.to(DEV), be.to(DEV), out=xi)
+    assert maxerr(xi, ref) < 1e-5
+
+
+@pytest.mark.parametrize("H,dh,Tq,Tk", [(16, 64, 70, 70), (8, 96, 33, 33), (2, 256, 12, 12), (1, 512, 64, 31),
+                                        (16, 64, 1, 200), (4, 128, 17, 65)])
+def test_attention(H, dh, Tq, Tk):
+    from megatts2_b200 import ops
+    g = gen(H * 1000 + dh + Tq)
+    B, D = 2, H * dh
+    q, k, v = (torch.randn(B, t, D, generator=g) for t in (Tq, Tk, Tk))
+
+    def ref_attn(mask):
+        qh = q.view(B, Tq, H, dh).transpose(1, 2).double()
+        kh = k.view(B, Tk, H, dh).transpose(1, 2).double()
+        vh = v.view(B, Tk, H, dh).transpose(1, 2).double()
+        s = qh @ kh.transpose(-1, -2) / math.sqrt(dh)
+        if mask is not None:
+            s = s + mask.double()
+        return (torch.softmax(s, -1) @ vh).transpose(1, 2).reshape(B, Tq, D)
+    y = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), H)
+    assert maxerr(y, ref_attn(None)) < 2e-5
+    if Tq == Tk:
+        m = R.attn_mask(torch.tensor([Tq, Tq], dtype=torch.int32), H, True)
+        y = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), H, m.to(DEV))
+        assert maxerr(y, ref_attn(m)) < 2e-5
+    pad = torch.zeros(B, 1, 1, Tk)
+    pad[1, ..., Tk // 2:] = float("-inf")
+    y = ops.attention(q.to(DEV), k.to(DEV), v.to(DEV), H, pad.to(DEV))
+    assert maxerr(y, ref_attn(pad)) < 2e-5
+    # strided (packed qkv) inputs
+    qkv = torch.cat([q, q, q], -1).to(DEV) if Tq == Tk else None
+    if qkv is not None:
+        y2 = ops.attention(qkv[..., :D], qkv[..., D:2 * D], qkv[..., 2 * D:], H)
+        qq = q
+        s = (qq.view(B, Tq, H, dh).transpose(1, 2).double() @ qq.view(B, Tq, H, dh).transpose(1, 2).double().transpose(-1, -2)) / math.sqrt(dh)
+        r2 = (torch.softmax(s, -1) @ qq.view(B, Tq, H, dh).transpose(1, 2).double()).transpose(1, 2).reshape(B, Tq, D)
+        assert maxerr(y2, r2) < 2e-5
+
+
+# ------------------------------------------------------------------------------ VQ
+def test_vq_search_golden(golden, weights_cpu):
+    from megatts2_b200 import ops
+    g = golden("vq_search")
+    embed = weights_cpu("g")["vqpe.vq.vq.layers.0._codebook.embed"].to(DEV)
+    idx = ops.vq_argmin(g["x"].to(DEV), embed).cpu()
+    ref = g["idx"]
+    mism = (idx != ref)
+    # a mismatch is only tolerated where fp64 itself says the two best codes are closer than fp32
+    # rounding of |x|^2 + |e|^2 ~ 500 (2 ulp ~ 6e-5); everywhere else the index must be bit-exact
+    assert bool((g["gap64"][mism] < 2e-4).all()), f"{int(mism.sum())} mismatches, gaps {g['gap64'][mism]}"
+    rate = 1.0 - mism.float().mean().item()
+    print(f"VQ-index bit-exact rate vs reference (adversarial fixture): {rate:.6f}")
+    assert rate > 0.97
+    assert torch.equal(idx[:512], ref[:512])                 # the random (non-adversarial) block
+    assert torch.equal(idx[-64:], torch.arange(64))          # exact codes map to themselves
+    dec = ops.vq_gather(ref.view(1, -1).to(DEV), embed)
+    assert torch.equal(dec.cpu()[0], embed.cpu()[ref])
+    rep = ops.vq_gather(ref[:10].view(2, 5).to(DEV), embed, t_out=37, repeat=8)
+    ref_rep = embed.cpu()[ref[:10].view(2, 5)].repeat_interleave(8, dim=1)[:, :37]
+    assert torch.equal(rep.cpu(), ref_rep)
+
+
+def test_vq_full_size_property(weights_cpu):
+    """C4-size search (64 x 64 rows): result must be the exact fp64 nearest code wherever the gap is clear,
+    and quantising a code row must return that code (idempotence)."""
+    from megatts2_b200 import ops
+    embed = weights_cpu("g")["vqpe.vq.vq.layers.0._codebook.embed"]
+    x = torch.randn(4096, 256, generator=gen(5))
+    idx = ops.vq_argmin(x.to(DEV), embed.to(DEV)).cpu()
+    d = torch.cdist(x.double(), embed.double()).pow(2)
+    top2 = d.topk(2, largest=False)
+    clear = (top2.values[:, 1] - top2.values[:, 0]) > 2e-4
+    assert torch.equal(idx[clear], top2.indices[clear, 0])
+    assert clear.float().mean() > 0.99
+    again = ops.vq_argmin(embed.to(DEV)[idx.to(DEV)], embed.to(DEV)).cpu()
+    assert torch.equal(again, idx)
+
+
+# ------------------------------------------------------------------------------ mel front end
+def test_mel_golden_and_oracle(golden):
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    g = golden("mel_frontend")
+    out = extract_mel_spec(g["wav"].to(DEV))
+    assert out.shape == (3, 80, 16)
+    assert maxerr(out, g["mel"]) < 5e-5                      # log-mel, fp32 FFT vs pocketfft fp32
+    assert (out.cpu() - g["mel"]).abs().mean().item() < 1e-5
+    wav = torch.rand(5, 48000, generator=gen(21)) * 2 - 1    # C2 shape: 3-s clips
+    ref = R.mel_spectrogram(wav)
+    out = extract_mel_spec(wav.to(DEV))
+    assert out.shape == (5, 80, 188)
+    assert (out.cpu() - ref).abs().mean().item() < 1e-5      # north-star: mel L1 <= 1e-4
+    assert maxerr(out, ref) < 1e-4
+    fm = extract_mel_spec(wav.to(DEV), frames_major=True)
+    assert torch.equal(fm.transpose(1, 2), out)
+    one = extract_mel_spec(wav[0].to(DEV))
+    assert torch.equal(one, out[0])
+    odd = torch.rand(2, 5000, generator=gen(22)) - 0.5       # frame count not a multiple of the CTA tile
+    assert maxerr(extract_mel_spec(odd.to(DEV)), R.mel_spectrogram(odd)) < 1e-4
+
+
+def test_mel_linear_domain_scaling_property():
+    """mel(a*x) = mel(x) + log(a) away from the clamp floor (the front end is linear before the log)."""
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    wav = torch.rand(64, 48000, generator=gen(23), device="cpu").to(DEV) * 2 - 1
+    a = extract_mel_spec(wav)
+    b = extract_mel_spec(wav * 0.25)
+    assert (b - (a + math.log(0.25))).abs().max().item() < 1e-4
+
+
+# ------------------------------------------------------------------------------ small ops
+def test_small_ops(golden):
+    from megatts2_b200 import ops
+    g = gen(31)
+    x = torch.randn(2, 61, 384, generator=g)
+    y = ops.maxpool_time(x.to(DEV), 8)
+    assert torch.equal(y.cpu(), F.max_pool1d(x.transpose(1, 2), 8, ceil_mode=True).transpose(1, 2))
+    ids = torch.randint(0, 320, (3, 17), generator=g)
+    tab = torch.randn(320, 512, generator=g)
+    pe = R.sine_pe_table(4000, 512)
+    e = ops.embed_pe(ids.to(DEV), tab.to(DEV), pe.to(DEV), 1.0)
+    assert maxerr(e, tab[ids] + pe[None, :17]) == 0.0
+    assert torch.equal(ops.add_pe(x[..., :512 - 128].contiguous().to(DEV), R.sine_pe_table(100, 384).to(DEV)).cpu(),
+                       x[..., :384] * 1.0 + R.sine_pe_table(100, 384)[None, :61])
+    lr = golden("length_regulator")
+    out, tot = ops.length_regulate(lr["x"].to(DEV), lr["d"].to(DEV))
+    assert out.shape == (2, 11, 128)                          # the reference's own test (modules/mrte.py:187-194)
+    assert torch.equal(out.cpu(), lr["y"]) and tot.tolist() == [10, 11]
+    d = torch.randint(0, 9, (4, 33), generator=g, dtype=torch.int32)
+    xx = torch.randn(4, 33, 512, generator=g)
+    out, tot = ops.length_regulate(xx.to(DEV), d.to(DEV))
+    assert torch.equal(out.cpu(), R.length_regulate(xx, d))
+    cf = torch.randn(3, 80, 45, generator=g)
+    cl = ops.to_channels_last(cf.to(DEV))
+    assert torch.equal(cl.cpu(), cf.transpose(1, 2))
+    assert torch.equal(ops.to_channels_first(cl).cpu(), cf)
+    padded = ops.to_channels_last(cf.to(DEV), pad_rep=5)
+    assert torch.equal(padded.cpu(), F.pad(cf, (5, 5), mode="replicate").transpose(1, 2))
+
+
+# ------------------------------------------------------------------------------ modules vs golden
+def test_encoder_golden(golden, G, PLM):
+    g = golden("encoder")
+    y = G.mrte.phone_encoder(g["x_phone"].to(DEV))
+    assert maxerr(y, g["y_phone"]) < 1e-4
+    lens = torch.tensor([7, 7], dtype=torch.int32, device=DEV)
+    assert maxerr(PLM.plm(g["x_plm"].to(DEV), lens, causal=True), g["y_plm_causal"]) < 2e-4
+    yn = PLM.plm(g["x_plm"].to(DEV))
+    assert maxerr(yn, g["y_plm_nomask"]) < 2e-4
+    from megatts2_b200.modules.transformer import run_encoder
+    last = run_encoder(PLM.plm, list(PLM.plm.layers), g["x_plm"].to(DEV), last_row_only=True)
+    assert last.shape == (2, 1, 1024)
+    assert maxerr(last[:, 0], g["y_plm_nomask"][:, -1]) < 2e-4     # exact pruning == full computation
+    # single layer + standalone MHA surfaces
+    l0 = PLM.plm.layers[0]
+    ref0 = R.encoder_layer(R.SD(weights.plm_state_dict(), "plm.layers.0."), g["x_plm"], 16, False)
+    assert maxerr(l0(g["x_plm"].to(DEV)), ref0) < 1e-4
+    ref_mha = R.mha(R.SD(weights.plm_state_dict(), "plm.layers.0.attn."), g["x_plm"], 16)
+    assert maxerr(l0.attn(g["x_plm"].to(DEV)), ref_mha) < 1e-4
+
+
+def test_vqpe_c1_bit_exact(golden, G):
+    g = golden("vqpe")
+    zq, commit, vql, codes = G.vqpe(g["mel1"].to(DEV))
+    assert codes.shape == (1, 1, 16) and codes.dtype == torch.int64
+    assert torch.equal(codes.cpu(), g["codes1"]), "C1: VQ code indices must be bit-exact"
+    assert maxerr(zq, g["zq1"]) <= 1e-5
+    assert commit.shape == (1, 1) and abs(float(vql) - float(g["vq_loss1"])) < 1e-3
+    ze, _ = G.vqpe.encode_cl(g["mel1"].to(DEV))
+    assert maxerr(ze.transpose(1, 2), g["ze1"]) < 2e-4
+    zq2, _, _, codes2 = G.vqpe(g["mel2"].to(DEV))
+    assert torch.equal(codes2.cpu(), g["codes2"]) and zq2.shape == (2, 61, 256)
+    assert maxerr(zq2, g["zq2"]) <= 1e-5
+    # reference-layout (B,C,T) surface of the conv stack
+    cn = G.vqpe.convnet(g["mel1"][..., :20].transpose(1, 2).to(DEV))
+    assert cn.shape == (1, 256, 16) and maxerr(cn, g["ze1"]) < 2e-4
+
+
+def test_mrte_golden(golden, G):
+    g = golden("mrte")
+    tc = G.mrte.tc_latent(g["phone"].to(DEV), g["mel"].to(DEV))
+    assert tc.shape == (2, 12, 512) and float(tc.min()) >= 0.0
+    assert maxerr(tc, g["tc_latent"]) < 2e-4
+    assert (tc.cpu() - g["tc_latent"]).abs().mean().item() < 2e-5
+    ctx = G.mrte.mel_encoder.forward_cl(g["mel"].to(DEV))
+    assert maxerr(ctx, g["mel_context"]) < 5e-4
+    tc3 = G.mrte.tc_latent(g["phone"].to(DEV), torch.tensor([12, 12], device=DEV), g["mel"].to(DEV))
+    assert torch.equal(tc3, tc)
+
+
+def test_adm_golden(golden, ADM):
+    g = golden("adm")
+    dur, raw = ADM.infer(g["tc_latent"].to(DEV), return_raw=True)
+    assert dur.shape == (2, 10, 1) and dur.dtype == torch.int32
+    assert maxerr(raw, g["raw"][..., 0]) < 2e-3
+    assert torch.equal(dur.cpu(), g["dur"]), "durations must match the reference exactly"
+    one = ADM.infer(g["tc_latent"][1:2].to(DEV))
+    assert torch.equal(one.cpu(), g["dur"][1:2])                  # batched == per-utterance
+    lens = torch.tensor([10, 10], dtype=torch.int32, device=DEV)
+    fwd, tgt = ADM(g["tc_latent"].to(DEV), g["dtok"].to(DEV), lens)
+    assert maxerr(fwd, g["fwd"]) < 2e-3
+
+
+def test_plm_golden(golden, PLM):
+    g = golden("plm")
+    ids, logits = PLM.infer(g["tc8"].to(DEV), return_logits=True)
+    assert ids.shape == (2, 12) and ids.dtype == torch.int64
+    assert torch.equal(ids.cpu(), g["ids"]), "PLM ids must be bit-exact"
+    assert maxerr(logits, g["logits"]) < 2e-3
+    ids1 = PLM.infer(g["tc8"][:1].to(DEV))
+    assert torch.equal(ids1.cpu(), g["ids"][:1])
+    pcodes = torch.cat([torch.full((2, 1), 1024), g["ids"]], 1).to(DEV)
+    lens = torch.tensor([12, 12], dtype=torch.int32, device=DEV)
+    f, tgt = PLM(g["tc8"].to(DEV), pcodes, lens)
+    assert maxerr(f, g["fwd_logits"]) < 2e-3 and torch.equal(tgt.cpu(), g["ids"])
+
+
+def test_hifigan_golden(golden, HIFI):
+    g = golden("hifigan")
+    wav = HIFI.decode_batch(g["mel"].to(DEV))
+    assert wav.shape == (2, 1, 256 * 22)
+    assert maxerr(wav, g["wav"]) < 1e-4                          # tanh output in [-1,1]
+    assert (wav.cpu() - g["wav"]).abs().mean().item() < 1e-5
+
+
+def test_e2e_golden(golden, weights_cpu):
+    g = golden("e2e")
+    tts = helpers.build_megatts(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), DEV)
+    o = tts.synthesize(g["phone"].to(DEV), g["mel_prompt"].to(DEV), forced_durations=g["dt_used"].to(DEV),
+                       return_intermediates=True)
+    assert torch.equal(o["dt"].cpu(), g["dt"])
+    assert torch.equal(o["p_codes"].cpu(), g["p_codes"])
+    assert maxerr(o["tc_latent"], g["tc_latent"]) < 2e-4
+    mel_cf = o["mel"].transpose(1, 2)
+    assert (mel_cf.cpu() - g["mel"]).abs().mean().item() < 1e-4   # north-star: mel L1 <= 1e-4
+    assert maxerr(mel_cf, g["mel"]) < 1e-3
+    assert maxerr(o["wav"], g["wav_oracle"]) < 1e-3
+    # free-running (ADM-predicted durations) gives the same thing when the clamp is not active
+    wav = tts.synthesize(g["phone"].to(DEV), g["mel_prompt"].to(DEV))
+    assert wav.shape[-1] == 256 * (int(g["dt"].sum()) + 10)
+
+
+def test_e2e_vs_oracle_batched(weights_cpu):
+    """B = 3 utterances, fresh seeded inputs, CUDA path vs the CPU oracle end to end."""
+    tts = helpers.build_megatts(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), DEV)
+    phone = torch.randint(0, 320, (3, 9), generator=gen(41))
+    melp = torch.randn(3, 80, 80, generator=gen(42)) * 2 - 4
+    forced = torch.randint(1, 7, (3, 9), generator=gen(43), dtype=torch.int32)
+    ref = R.synthesize(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), phone, melp,
+                       (weights.G_CFG, weights.PLM_CFG, weights.ADM_CFG, weights.HIFIGAN_CFG), forced_durations=forced)
+    o = tts.synthesize(phone.to(DEV), melp.to(DEV), forced_durations=forced.to(DEV), return_intermediates=True)
+    assert torch.equal(o["dt"].cpu(), ref["dt"])
+    # the oracle pads ragged utterances exactly like the reference's LengthRegulator (zeros up to the
+    # longest one), so the whole batch - padding included - must agree
+    assert torch.equal(o["p_codes"].cpu(), ref["p_codes"])
+    assert maxerr(o["tc_latent"], ref["tc_latent"]) < 2e-4
+    assert (o["mel"].cpu() - ref["mel"].transpose(1, 2)).abs().mean().item() < 1e-4
+    assert maxerr(o["wav"], ref["wav"]) < 1e-3
+
+
+def test_batch_invariance_property(weights_cpu, PLM):
+    """Sharding property behind the multi-GPU split: any sub-batch gives bit-identical ids."""
+    tc8 = F.relu(torch.randn(8, 16, 512, generator=gen(51))).to(DEV)
+    full = PLM.infer(tc8)
+    parts = torch.cat([PLM.infer(tc8[:3]), PLM.infer(tc8[3:])], 0)
+    assert torch.equal(full, parts)
+    assert torch.equal(full, PLM.infer(tc8))                    # deterministic

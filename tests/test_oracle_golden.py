@@ -1,0 +1,132 @@
+"""CPU: the oracle restatement (oracle/ref_megatts2.py) against the fixtures produced by the
+REAL reference (tests/golden/*.npz, written by oracle/make_golden.py in the build container).
+This is what pins the oracle; the GPU parity tests then compare the CUDA path to the oracle
+and to the same fixtures."""
+import json
+import os
+
+import pytest
+import torch
+
+from oracle import ref_megatts2 as R
+from oracle import weights
+
+from conftest import GOLDEN
+
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+
+
+def test_state_dict_keys_match_reference():
+    with open(os.path.join(GOLDEN, "state_dict_keys.json")) as f:
+        ref = json.load(f)
+    for name, spec in (("G", weights.g_spec()), ("plm", weights.plm_spec()), ("adm", weights.adm_spec())):
+        assert list(spec.keys()) == list(ref[name].keys()), name
+        assert {k: list(v) for k, v in spec.items()} == ref[name], name
+    assert len(ref["G"]) == 840
+
+
+def test_mel_frontend(golden):
+    g = golden("mel_frontend")
+    out = R.mel_spectrogram(g["wav"])
+    assert out.shape == g["mel"].shape == (3, 80, 16)
+    assert (out - g["mel"]).abs().max() < 2e-5
+    # the silent clip sits on the clamp floor log(1e-5)
+    assert torch.allclose(out[2], torch.full_like(out[2], -11.512925), atol=1e-4)
+
+
+def test_filterbank_vs_torchaudio():
+    ta = pytest.importorskip("torchaudio")
+    fb = ta.functional.melscale_fbanks(513, 0.0, 8000.0, 80, 16000, norm="slaney", mel_scale="slaney")
+    mine = R.slaney_fbanks()
+    assert (mine - fb).abs().max() < 2e-7
+    assert int((mine != 0).sum()) == 1001
+
+
+def test_vqpe_c1_bit_exact(golden, weights_cpu):
+    g = golden("vqpe")
+    sd = R.SD(weights_cpu("g"), "vqpe.")
+    zq, commit, vql, codes, ze = R.vqpe_forward(sd, g["mel1"], weights.G_CFG)
+    assert torch.equal(codes, g["codes1"]) and codes.shape == (1, 1, 16)
+    assert (zq - g["zq1"]).abs().max() <= 1e-5
+    assert (ze - g["ze1"]).abs().max() <= 1e-4
+    assert abs(float(vql) - float(g["vq_loss1"])) < 1e-4
+    zq2, _, _, codes2, _ = R.vqpe_forward(sd, g["mel2"], weights.G_CFG)
+    assert torch.equal(codes2, g["codes2"]) and zq2.shape == (2, 61, 256)
+
+
+def test_vq_search(golden, weights_cpu):
+    g = golden("vq_search")
+    embed = weights_cpu("g")["vqpe.vq.vq.layers.0._codebook.embed"]
+    assert torch.equal(R.vq_quantize(g["x"], embed), g["idx"])
+
+
+def test_encoders(golden, weights_cpu):
+    g = golden("encoder")
+    y = R.encoder(R.SD(weights_cpu("g"), "mrte.phone_encoder."), g["x_phone"], 8, 2, True)
+    assert (y - g["y_phone"]).abs().max() < 2e-4
+    psd = R.SD(weights_cpu("plm"), "plm.")
+    lens = torch.tensor([7, 7], dtype=torch.int32)
+    assert (R.encoder(psd, g["x_plm"], 12, 16, False, lens=lens, causal=True) - g["y_plm_causal"]).abs().max() < 5e-4
+    assert (R.encoder(psd, g["x_plm"], 12, 16, False) - g["y_plm_nomask"]).abs().max() < 5e-4
+
+
+def test_mrte(golden, weights_cpu):
+    g = golden("mrte")
+    tc, ctx, _ = R.mrte_tc_latent(R.SD(weights_cpu("g"), "mrte."), g["phone"], g["mel"], weights.G_CFG)
+    assert (tc - g["tc_latent"]).abs().max() < 2e-4
+    assert (ctx - g["mel_context"]).abs().max() < 2e-4
+    assert float(tc.min()) >= 0.0
+
+
+def test_length_regulator_reference_case(golden):
+    g = golden("length_regulator")
+    y = R.length_regulate(g["x"], g["d"])
+    assert y.shape == (2, 11, 128)          # the reference's own assertion (modules/mrte.py:187-194)
+    assert torch.equal(y, g["y"])
+
+
+def test_adm(golden, weights_cpu):
+    g = golden("adm")
+    dur, raw = R.adm_infer(R.SD(weights_cpu("adm")), g["tc_latent"], weights.ADM_CFG, return_raw=True)
+    assert torch.equal(dur, g["dur"])
+    assert (raw - g["raw"]).abs().max() < 2e-3
+    fwd, _ = R.adm_forward(R.SD(weights_cpu("adm")), g["tc_latent"], g["dtok"],
+                           torch.tensor([10, 10], dtype=torch.int32), weights.ADM_CFG)
+    assert (fwd - g["fwd"]).abs().max() < 2e-3
+
+
+def test_plm(golden, weights_cpu):
+    g = golden("plm")
+    ids, lg = R.plm_infer(R.SD(weights_cpu("plm")), g["tc8"], weights.PLM_CFG, return_logits=True)
+    assert torch.equal(ids, g["ids"])
+    assert (lg - g["logits"]).abs().max() < 2e-3
+    assert ids.unique().numel() >= 8        # the fixture is not degenerate
+
+
+def test_e2e_body(golden, weights_cpu):
+    g = golden("e2e")
+    o = R.synthesize(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), g["phone"],
+                     g["mel_prompt"], (weights.G_CFG, weights.PLM_CFG, weights.ADM_CFG, weights.HIFIGAN_CFG),
+                     forced_durations=g["dt_used"])
+    assert torch.equal(o["dt"], g["dt"]) and torch.equal(o["p_codes"], g["p_codes"])
+    assert (o["mel"] - g["mel"]).abs().mean() < 1e-4
+    assert (o["wav"] - g["wav_oracle"]).abs().max() < 1e-5
+
+
+def test_hifigan_shape_and_regression(golden, weights_cpu):
+    g = golden("hifigan")
+    wav = R.hifigan_generator(weights_cpu("hifigan"), g["mel"], weights.HIFIGAN_CFG)
+    assert wav.shape == (2, 1, 256 * (12 + 10))
+    assert (wav - g["wav"]).abs().max() < 1e-5
+    n = sum(v.numel() for v in weights_cpu("hifigan").values())
+    assert n == 13_926_017                 # HiFi-GAN V1 generator size
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/modules"), reason="reference tree not present (GPU box)")
+def test_reference_loads_oracle_weights_strict():
+    """Container only: the real reference accepts the oracle's state dicts with strict=True."""
+    from oracle import stubs
+    G, plm, adm = stubs.build_reference_models()
+    G.load_state_dict(weights.g_state_dict(), strict=True)
+    plm.load_state_dict(weights.plm_state_dict(), strict=True)
+    adm.load_state_dict(weights.adm_state_dict(), strict=True)
