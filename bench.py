@@ -1,0 +1,390 @@
+#!/usr/bin/env python
+"""bench.py - synthesized audio samples/sec @ batch 64 (BASELINE.json metric, config C4).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference]
+
+One "step" = one pass of the synthesis hot path over one batch of 64 synthetic utterances U
+(64 phones, 8-s prompt -> 500 mel frames, durations forced to 8 -> 512 mel
+frames -> 64 prosody tokens -> 131,072 samples):  mel front end (STFT+mel) -> MRTE ->
+ADM autoregressive decode -> length regulator -> max-pool -> PLM autoregressive decode ->
+VQ decode + mel decoder -> HiFi-GAN.  Weights: seeded random init of the reference
+architecture (no checkpoints exist offline); data: synthetic.  N > 1: one process per GPU
+(torchrun), every rank synthesises its own 64 utterances (weak scaling, no data-path
+collective; NCCL only for the barrier / max-over-ranks of the timing).
+
+Output: ONE JSON line (contract in the task statement) with `roofline`, `cpu_baseline`, `e2e`,
+`clocks`, `gpu_launches`.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+B_PER_GPU = 64
+TP, TM_FRAMES, DUR = 64, 500, 8
+PROMPT_SAMPLES = (TM_FRAMES - 1) * 256 + 128          # 1 + L // 256 == 500
+SAMPLES_PER_UTT = TP * DUR * 256                      # 131,072 mel-aligned samples (the vocoder also emits 10 pad frames)
+METRIC = "synthesized_audio_samples_per_sec_batch64"
+UNIT = "samples/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default: the C4 batch, 64)")
+    ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU leg (profiling runs)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads for the CPU legs (0 = calibrate)")
+    return ap.parse_args()
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def pick_cpu_threads(requested=0):
+    """The CPU legs are the reference's batch-1 AR loops: thousands of small ops.  With every hardware thread
+    of a many-core host the OpenMP fork/join cost dominates, so calibrate on a representative op (one
+    64-row x 1024 x 4096 GEMM + LayerNorm) and keep the fastest power-of-two thread count."""
+    ncpu = os.cpu_count() or 1
+    if requested > 0:
+        return min(requested, ncpu)
+    x = torch.randn(64, 1024)
+    w = torch.randn(4096, 1024)
+    best, best_t = 1, float("inf")
+    n = 1
+    cands = []
+    while n < ncpu:
+        cands.append(n)
+        n *= 2
+    cands.append(ncpu)
+    for n in cands:
+        torch.set_num_threads(n)
+        for _ in range(3):
+            torch.nn.functional.layer_norm(torch.nn.functional.linear(x, w), (4096,))
+        t0 = time.perf_counter()
+        for _ in range(20):
+            torch.nn.functional.layer_norm(torch.nn.functional.linear(x, w), (4096,))
+        dt = time.perf_counter() - t0
+        if dt < best_t * 0.97:
+            best, best_t = n, dt
+    return best
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return d, "measured"
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc, self.thr = index, [], None, None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "200", "-i", str(self.index)], stdout=subprocess.PIPE, text=True)
+        except Exception:
+            self.proc = None
+            return
+        self.thr = threading.Thread(target=self._read, daemon=True)
+        self.thr.start()
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+def build_product(device):
+    """Random-init (seeded) product modules of the reference architecture; no oracle import here."""
+    import yaml
+    from megatts2_b200.models.megatts2 import HIFIGAN, MegaG, Megatts
+    from megatts2_b200.utils.utils import instantiate_class
+    cfg = os.path.join(ROOT, "configs")
+    torch.manual_seed(0)
+    G = MegaG.from_hparams(os.path.join(cfg, "config_gan.yaml"))
+    cb = G.vqpe.vq.vq.layers[0]._codebook
+    cb.embed.normal_()
+    cb.embed_avg.copy_(cb.embed)
+    cb.inited.fill_(1.0)
+    torch.manual_seed(1)
+    plm = instantiate_class((), yaml.safe_load(open(os.path.join(cfg, "config_plm.yaml")))["model"]["plm"])
+    torch.manual_seed(2)
+    adm = instantiate_class((), yaml.safe_load(open(os.path.join(cfg, "config_adm.yaml")))["model"]["adm"])
+    with torch.no_grad():    # keep the AR duration regression bounded on random weights
+        adm.dt_linear_emb.weight.mul_(0.02)
+    torch.manual_seed(3)
+    hifi = HIFIGAN.from_hparams()
+    return Megatts(generator=G, plm=plm, adm=adm, hifi_gan=hifi, device=device)
+
+
+def make_inputs(batch, seed):
+    g = torch.Generator().manual_seed(seed)
+    wav = torch.rand(batch, PROMPT_SAMPLES, generator=g) * 2 - 1
+    phone = torch.randint(0, 320, (batch, TP), generator=g)
+    if torch.cuda.is_available():
+        wav, phone = wav.pin_memory(), phone.pin_memory()
+    forced = torch.full((batch, TP), DUR, dtype=torch.int32)
+    return wav, phone, forced
+
+
+def gpu_step(tts, wav_d, phone_d, forced_d):
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    mel = extract_mel_spec(wav_d, frames_major=True)                  # (B, 500, 80)
+    return tts.synthesize(phone_d, mel, forced_durations=forced_d)     # (B, 1, 133632)
+
+
+def run_b200(args):
+    from megatts2_b200 import _lib as L
+    from megatts2_b200 import ops
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.batch
+    log("building product modules")
+    tts = build_product(dev)
+    wav_h, phone_h, forced = make_inputs(B, 1234 + rank)
+    wav_d, phone_d, forced_d = wav_h.to(dev), phone_h.to(dev), forced.to(dev)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
+    out_h = torch.empty(B, 1, 256 * (TP * DUR + 10), dtype=torch.float32).pin_memory()
+    lib = L.lib()
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (also builds the packed-weight plans and grows the workspace)
+    for _ in range(max(args.warmup, 1)):
+        out = gpu_step(tts, wav_d, phone_d, forced_d)
+    torch.cuda.synchronize()
+    log("warm-up done")
+
+    # ---- timed region 1: device-resident inputs (`value`)
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    n0 = ops.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        flush.zero_()                                                   # L2 flush between timed iterations
+        out = gpu_step(tts, wav_d, phone_d, forced_d)
+    e1.record()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    launches = ops.launch_count() - n0
+    ms = e0.elapsed_time(e1)
+    log(f"timed region: {ms / args.steps:.1f} ms/step")
+
+    # ---- timed region 2: end to end through the public API with HOST buffers (`e2e`)
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        flush.zero_()
+        w = wav_h.to(dev, non_blocking=True)
+        ph = phone_h.to(dev, non_blocking=True)
+        out = gpu_step(tts, w, ph, forced_d)
+        out_h.copy_(out, non_blocking=True)
+    f1.record()
+    barrier()
+    ms_e2e = f0.elapsed_time(f1)
+    log(f"e2e region: {ms_e2e / args.steps:.1f} ms/step")
+
+    if dist is not None:
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = t.tolist()
+    total_samples = world * B * SAMPLES_PER_UTT * args.steps
+    value = total_samples / (ms / 1e3)
+    e2e_value = total_samples / (ms_e2e / 1e3)
+
+    result = None
+    if rank == 0:
+        # ---- roofline leg: per-launch CUDA events around every tap-GEMM launch of ONE step
+        lib.mtts_profile_begin()
+        gpu_step(tts, wav_d, phone_d, forced_d)
+        gms, gfl, gn = C.c_double(), C.c_double(), C.c_int64()
+        L.check(lib.mtts_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn)))
+        log(f"roofline leg: {gn.value} tap-GEMM launches, {gms.value:.1f} ms, {gfl.value / 1e12:.2f} TFLOP")
+        pk, pk_src = peaks()
+        peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
+        achieved = gfl.value / (gms.value / 1e3) / 1e12 if gms.value > 0 else 0.0
+        roofline = {"bound": "tensor", "kernel": "tapconv_kernel (fp32 FFMA tap-GEMM: all Linear/Conv1d/ConvTranspose1d)",
+                    "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
+                    "traffic": None, "peak_source": f"{pk_src} bf16 dense (sustained); the kernel runs exact fp32 FFMA",
+                    "gemm_ms_per_step": round(gms.value, 2), "gemm_tflop_per_step": round(gfl.value / 1e12, 3),
+                    "gemm_launches_per_step": gn.value, "gemm_share_of_step": round(gms.value / (ms / args.steps), 3)}
+        cpu = None if args.no_cpu_baseline else cpu_baseline(tts, args)
+        result = {
+            "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4: full synthesis MRTE+ADM+PLM+decoder+HiFi-GAN (+mel front end), "
+                                   f"batch {B} synthetic utterances per GPU (64 phones, 500-frame prompt, "
+                                   "512 mel frames, 64 prosody tokens, 131072 samples each)",
+                       "global_batch": world * B, "parallelism": f"replicas x{world} (batch split, no data-path collective)",
+                       "l2": "256 MiB flush write between timed iterations; working set (1.57 GB weights) >> 126 MB L2",
+                       "weights": "seeded random init of the reference architecture", "ar_semantics": "reference-faithful "
+                       "non-causal full recompute per step (models/megatts2.py:165-181, 257-275)"},
+            "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 3),
+                    "h2d_bytes_per_step": world * (wav_h.numel() * 4 + phone_h.numel() * 8),
+                    "d2h_bytes_per_step": world * out_h.numel() * 4},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+        }
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+    return result
+
+
+def cpu_baseline(tts, args, n_utt=2):
+    """The oracle port (CPU restatement of the reference, batch 1 like the reference) timed on this box's
+    host cores on a bounded sample of the same workload, and used as the CHECKER of the GPU arm's ids /
+    mel on that sample (same weights: the product's state dicts copied to the host)."""
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    cores = pick_cpu_threads(args.cpu_threads)
+    torch.set_num_threads(cores)
+    log(f"cpu_baseline: {cores} torch threads of {os.cpu_count()} host cpus")
+    sd = {k: {n: v.detach().cpu() for n, v in m.state_dict().items()}
+          for k, m in (("g", tts.generator), ("plm", tts.plm), ("adm", tts.adm), ("h", tts.hifi_gan.generator))}
+    wav, phone, forced = make_inputs(n_utt, 99)
+    dev = next(tts.parameters()).device
+    gpu = gpu_step_intermediates(tts, wav.to(dev), phone.to(dev), forced.to(dev))
+    cfgs = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
+    t0 = time.perf_counter()
+    exact_ids = exact_dur = n_ids = n_dur = 0
+    mel_l1 = 0.0
+    for u in range(n_utt):
+        mel = R.mel_spectrogram(wav[u:u + 1]).transpose(1, 2)
+        ref = R.synthesize(sd["g"], sd["plm"], sd["adm"], sd["h"], phone[u:u + 1], mel, cfgs,
+                           forced_durations=forced[u:u + 1])
+        log(f"cpu_baseline: utterance {u + 1}/{n_utt} done at {time.perf_counter() - t0:.1f} s")
+        exact_ids += int((ref["p_codes"] == gpu["p_codes"][u:u + 1].cpu()).sum()); n_ids += ref["p_codes"].numel()
+        exact_dur += int((ref["dt"] == gpu["dt"][u:u + 1].cpu()).sum()); n_dur += ref["dt"].numel()
+        mel_l1 += (ref["mel"].transpose(1, 2) - gpu["mel"][u:u + 1].cpu()).abs().mean().item() / n_utt
+    dt = time.perf_counter() - t0
+    return {"value": round(n_utt * SAMPLES_PER_UTT / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{n_utt} of the {args.batch} utterances U, batch 1 each (the reference's infer() is batch-1 only), "
+                      f"{dt:.1f} s of CPU time, torch threads = {cores} (fastest of the calibrated counts on "
+                      f"{os.cpu_count()} host cpus)",
+            "rtf": round(dt / (n_utt * SAMPLES_PER_UTT / 16000.0), 3),
+            "parity_on_sample": {"plm_id_exact_rate": exact_ids / max(n_ids, 1), "duration_exact_rate": exact_dur / max(n_dur, 1),
+                                 "mel_l1": mel_l1}}
+
+
+def gpu_step_intermediates(tts, wav_d, phone_d, forced_d):
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    mel = extract_mel_spec(wav_d, frames_major=True)
+    o = tts.synthesize(phone_d, mel, forced_durations=forced_d, return_intermediates=True)
+    torch.cuda.synchronize()
+    return o
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference
+    cannot be pip-installed - it has no setup.py / pyproject and needs un-vendored speechbrain) on this box's
+    host cores, batch 1 as infer.py does, each step = one utterance U."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    cores = pick_cpu_threads(args.cpu_threads)
+    torch.set_num_threads(cores)
+    log(f"reference arm: {cores} torch threads of {os.cpu_count()} host cpus")
+    wg, wp, wa, wh = W.g_state_dict(), W.plm_state_dict(), W.adm_state_dict(), W.hifigan_state_dict()
+    cfgs = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
+    wav, phone, forced = make_inputs(1, 1234)
+
+    def step():
+        mel = R.mel_spectrogram(wav).transpose(1, 2)
+        return R.synthesize(wg, wp, wa, wh, phone, mel, cfgs, forced_durations=forced)["wav"]
+    for _ in range(min(args.warmup, 1)):       # one warm-up pass is enough on the CPU (each is ~10 s)
+        step()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step()
+        log(f"reference arm: step {i + 1}/{args.steps} at {time.perf_counter() - t0:.1f} s")
+    dt = time.perf_counter() - t0
+    v = args.steps * SAMPLES_PER_UTT / dt
+    return {"impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "C4 utterance U through the reference's CPU path (oracle port), batch 1 per step "
+                                   "(the reference's infer() loops are batch-1 only)"},
+            "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": f"{args.steps} x 1 utterance U (131072 samples) per step, torch threads = {cores} "
+                                       f"(fastest calibrated count on {os.cpu_count()} host cpus)"},
+            "e2e": {"value": round(v, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        res = run_reference(args)
+    else:
+        if not torch.cuda.is_available():
+            print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path only (no CPU fallback)"}))
+            return 1
+        res = run_b200(args)
+    if res is not None:
+        print(json.dumps(res))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

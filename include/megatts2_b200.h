@@ -79,6 +79,16 @@ typedef struct {
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);
 
+/* Tensor-core linear layer (tcgen05, sm_100a): Y[M,N] = post(pre(X)[M,K] . W[N,K]^T + bias) (+ R) with
+ * fp32-grade accuracy from a 3-way bf16 split of both operands and 6 MMAs (x1w1 + x1w2 + x2w1 + x2w2 +
+ * x1w3 + x3w1, fp32 accumulation in TMEM).  w_planes: (3, N, K) bf16 row-major; scratch receives the
+ * activation planes (mtts_linear_tc_scratch_bytes(rows_cap, K), rows_cap >= M).  K %% 8 == 0. */
+int64_t mtts_linear_tc_scratch_bytes(int64_t rows_cap, int32_t K);
+int mtts_linear_tc_f32(const float* x, int32_t ldx, int64_t M, int32_t K, const void* w_planes, int32_t N,
+                       const float* bias, const float* res, int32_t ldr, float* y, int32_t ldy,
+                       int32_t pre_act, float pre_slope, int32_t post_act,
+                       void* scratch, int64_t scratch_bytes, int64_t rows_cap, void* stream);
+
 /* LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; modules/convnet.py:28-30,
  * modules/transformer.py:67-68, modules/mrte.py:136):
  *   v = LN(x[row]) * gamma + beta;  v = post(v);  v += res[row];  v += y_old (accumulate) */
@@ -162,10 +172,14 @@ typedef struct {
   const float *w_o, *b_o;              /* (1, D, D), (D) */
   const float *w_ff1, *b_ff1;          /* linear: (1, D, F); conv-FF: (5, D, F) */
   const float *w_ff2, *b_ff2;          /* linear: (1, F, D); conv-FF: (5, F, D) */
+  /* tensor-core engine (optional, linear layers only): the same weights as THREE bf16 planes
+   * (3, N, K) row-major (w = w1 + w2 + w3, see mtts_linear_tc_f32); NULL -> exact FFMA engine */
+  const void *w_qkv_tc, *w_o_tc, *w_ff1_tc, *w_ff2_tc;
 } mtts_encoder_layer;
 
 typedef struct {
   int32_t n_layers, d_model, n_heads, ff_dim, conv_ff;
+  int32_t engine;                      /* 0: fp32 FFMA everywhere; 1: tcgen05 bf16x3 for GEMMs with M >= 128 */
   const mtts_encoder_layer* layers;    /* HOST array of n_layers entries */
 } mtts_encoder;
 

@@ -47,12 +47,12 @@ class AttnParams(C.Structure):
 class EncoderLayer(C.Structure):
     _fields_ = [(n, vp) for n in (
         "ln1_g", "ln1_b", "ln2_g", "ln2_b", "w_qkv", "b_qkv", "w_o", "b_o",
-        "w_ff1", "b_ff1", "w_ff2", "b_ff2")]
+        "w_ff1", "b_ff1", "w_ff2", "b_ff2", "w_qkv_tc", "w_o_tc", "w_ff1_tc", "w_ff2_tc")]
 
 
 class Encoder(C.Structure):
     _fields_ = [("n_layers", i32), ("d_model", i32), ("n_heads", i32), ("ff_dim", i32), ("conv_ff", i32),
-                ("layers", C.POINTER(EncoderLayer))]
+                ("engine", i32), ("layers", C.POINTER(EncoderLayer))]
 
 
 class PLM(C.Structure):
@@ -102,6 +102,8 @@ SIGNATURES = {
     "mtts_profile_begin": (C.c_int, []),
     "mtts_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "mtts_conv1d_f32": (C.c_int, [C.POINTER(ConvParams), vp]),
+    "mtts_linear_tc_scratch_bytes": (i64, [i64, i32]),
+    "mtts_linear_tc_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, vp, i64, i64, vp]),
     "mtts_layernorm_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, f32, i32, i32, vp]),
     "mtts_attention_f32": (C.c_int, [C.POINTER(AttnParams), vp]),
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),

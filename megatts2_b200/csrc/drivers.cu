@@ -28,6 +28,42 @@ int conv1d(const mtts_conv_params& p, cudaStream_t st) {
   return rc;
 }
 
+// scratch for the tensor-core engine's activation planes, carved once per driver call so that the
+// (cached) TMA descriptors keep hitting across the steps of an autoregressive loop
+struct TcScratch { void* p; int64_t bytes; int64_t rows_cap; };
+
+static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
+  if (e->engine != 1 || e->conv_ff) return 0;
+  const int kmax = e->ff_dim > e->d_model ? e->ff_dim : e->d_model;
+  return linear_tc_scratch_bytes(rows_cap, kmax) + 1024;
+}
+
+// dense layer dispatch: tcgen05 bf16x3 when enabled, packed planes exist and the tile is worth it
+static int lin(const mtts_encoder* e, const TcScratch* tc, const float* x, int ldx, int64_t M, int K, int N,
+               const float* w32, const void* wtc, const float* bias, const float* res, int ldr, float* y, int ldy,
+               int post_act, cudaStream_t st) {
+  if (e->engine == 1 && tc && tc->p && wtc && M >= 128 && K % 8 == 0 && N % 4 == 0) {
+    ProfRec r;
+    const bool prof = g_prof_on;
+    if (prof) {
+      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+      r.flops = 2.0 * (double)M * N * K;
+      cudaEventRecord(r.a, st);
+    }
+    const int rc = linear_tc(x, ldx, M, K, wtc, N, bias, res, ldr, y, ldy, 0, 0.f, post_act, 1.0f, tc->p, tc->bytes,
+                             tc->rows_cap, st);
+    if (prof) {
+      cudaEventRecord(r.b, st);
+      std::lock_guard<std::mutex> lk(g_prof_mu);
+      g_prof.push_back(r);
+    }
+    return rc;
+  }
+  mtts_conv_params p = linear_params(x, ldx, w32, bias, y, ldy, M, K, N);
+  p.res = res; p.ldr = ldr; p.post_act = post_act;
+  return conv1d(p, st);
+}
+
 // ------------------------------------------------------------------------------------------
 // TransformerEncoder.forward (modules/transformer.py:88-102, 119-133)
 static int64_t encoder_ws_floats(const mtts_encoder* e, int B, int T) {
@@ -38,7 +74,7 @@ static int64_t encoder_ws_floats(const mtts_encoder* e, int B, int T) {
 
 static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int B, int T, const float* mask,
                            int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, int last_row_only, Arena& ar,
-                           cudaStream_t st) {
+                           const TcScratch* tc, cudaStream_t st) {
   const int D = e->d_model, H = e->n_heads, F = e->ff_dim, dh = D / H;
   MTTS_REQUIRE(D % H == 0, "d_model not divisible by n_heads");
   MTTS_REQUIRE(!(last_row_only && e->conv_ff), "last_row_only needs a linear feed-forward");
@@ -58,10 +94,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
     const bool last = last_row_only && (l == e->n_layers - 1);
     // h = LN1(x);  qkv = h Wqkv + b
     MTTS_TRY(layernorm(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
-    {
-      mtts_conv_params p = linear_params(h, D, L.w_qkv, L.b_qkv, qkv, 3 * D, M, D, 3 * D);
-      MTTS_TRY(conv1d(p, st));
-    }
+    MTTS_TRY(lin(e, tc, h, D, M, D, 3 * D, L.w_qkv, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, st));
     mtts_attn_params ap;
     memset(&ap, 0, sizeof(ap));
     ap.B = B; ap.H = H; ap.Tk = T; ap.dh = dh; ap.scale = scale;
@@ -73,9 +106,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       ap.o = a; ap.o_sb = (int64_t)T * D; ap.o_st = D;
       MTTS_TRY(attention(ap, st));
       // x = x + a Wo + bo
-      mtts_conv_params p = linear_params(a, D, L.w_o, L.b_o, xw, D, M, D, D);
-      p.res = xin; p.ldr = D;
-      MTTS_TRY(conv1d(p, st));
+      MTTS_TRY(lin(e, tc, a, D, M, D, D, L.w_o, L.w_o_tc, L.b_o, xin, D, xw, D, 0, st));
       if (e->conv_ff) {
         // x = LN2(x); x = x + conv5(relu(conv5(x)))       (transformer.py:96-98)
         MTTS_TRY(layernorm(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, xw, D, M, D, 1e-5f, 0, 0, st));
@@ -88,12 +119,8 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       } else {
         // x = x + W2 relu(W1 LN2(x) + b1) + b2             (transformer.py:101)
         MTTS_TRY(layernorm(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
-        mtts_conv_params p1 = linear_params(h, D, L.w_ff1, L.b_ff1, f, F, M, D, F);
-        p1.post_act = MTTS_ACT_RELU;
-        MTTS_TRY(conv1d(p1, st));
-        mtts_conv_params p2 = linear_params(f, F, L.w_ff2, L.b_ff2, xw, D, M, F, D);
-        p2.res = xw; p2.ldr = D;
-        MTTS_TRY(conv1d(p2, st));
+        MTTS_TRY(lin(e, tc, h, D, M, D, F, L.w_ff1, L.w_ff1_tc, L.b_ff1, nullptr, 0, f, F, MTTS_ACT_RELU, st));
+        MTTS_TRY(lin(e, tc, f, F, M, F, D, L.w_ff2, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, st));
       }
       xin = xw;
     } else {
@@ -127,7 +154,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
 // MegaPLM.infer (models/megatts2.py:165-181)
 static int64_t plm_ws_floats(const mtts_plm* m, int B, int T) {
   const int64_t D = m->enc.d_model;
-  return encoder_ws_floats(&m->enc, B, T) + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * m->vq_bins +
+  return encoder_ws_floats(&m->enc, B, T) + tc_scratch_bytes(&m->enc, (int64_t)B * T) / 4 + 512 + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * m->vq_bins +
          2 * ((int64_t)B * (T + 1) + 64) + 6 * 64;
 }
 
@@ -142,6 +169,8 @@ static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_l
   float* xl = top.take<float>((int64_t)B * D);
   float* logits = top.take<float>((int64_t)B * V);
   int64_t* codes = top.take<int64_t>((int64_t)B * (T + 1));
+  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T};
+  if (tcs.bytes) tcs.p = top.take<char>(tcs.bytes);
   const int64_t enc_off = align_up(top.off, 256);
   if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
     return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "plm_infer",
@@ -152,7 +181,7 @@ static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_l
     MTTS_TRY(plm_build_input(tc, tc_sb, tc_ld, m->tc_dim, codes, T + 1, m->pc_embedding, m->vq_dim, V + 2, m->pe,
                              m->pe_alpha, B, S, X, st));
     Arena ar((char*)ws + enc_off, ws_bytes - enc_off);
-    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, st));
+    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, &tcs, st));
     float* lg = logits_out ? logits_out + (int64_t)t * V : logits;
     const int64_t lg_sb = logits_out ? (int64_t)T * V : V;
     mtts_conv_params p;
@@ -171,7 +200,7 @@ static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_l
 // MegaADM.infer (models/megatts2.py:257-275)
 static int64_t adm_ws_floats(const mtts_adm* m, int B, int T) {
   const int64_t D = m->enc.d_model;
-  return encoder_ws_floats(&m->enc, B, T) + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * T * m->tc_emb_dim +
+  return encoder_ws_floats(&m->enc, B, T) + tc_scratch_bytes(&m->enc, (int64_t)B * T) / 4 + 512 + (int64_t)B * T * D + (int64_t)B * D + (int64_t)B * T * m->tc_emb_dim +
          (int64_t)B * (T + 1) + 6 * 64;
 }
 
@@ -186,6 +215,8 @@ static int adm_infer(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_l
   float* xl = top.take<float>((int64_t)B * D);
   float* tc_emb = top.take<float>((int64_t)B * T * m->tc_emb_dim);
   float* praw = top.take<float>((int64_t)B * (T + 1));
+  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T};
+  if (tcs.bytes) tcs.p = top.take<char>(tcs.bytes);
   const int64_t enc_off = align_up(top.off, 256);
   if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
     return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "adm_infer",
@@ -207,7 +238,7 @@ static int adm_infer(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_l
     MTTS_TRY(adm_build_input(tc_emb, (int64_t)T * m->tc_emb_dim, m->tc_emb_dim, m->tc_emb_dim, praw, T + 1, m->w_dt,
                              m->emb_dim, m->pe, m->pe_alpha, B, S, X, st));
     Arena ar((char*)ws + enc_off, ws_bytes - enc_off);
-    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, st));
+    MTTS_TRY(encoder_forward(&m->enc, X, xl, B, S, nullptr, 0, 0, 0, 1, ar, &tcs, st));
     MTTS_TRY(adm_readout(xl, D, m->w_predict, B, praw, T + 1, t + 1, st));
   }
   MTTS_TRY(adm_finalize(praw, T + 1, B, T, dur_out, raw_out, st));
@@ -457,14 +488,26 @@ int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches
 }
 
 int64_t mtts_encoder_workspace_bytes(const mtts_encoder* enc, int32_t B, int32_t T) {
-  return encoder_ws_floats(enc, B, T) * 4 + 4096;
+  return encoder_ws_floats(enc, B, T) * 4 + tc_scratch_bytes(enc, (int64_t)B * T) + 8192;
 }
 int mtts_encoder_forward_f32(const mtts_encoder* enc, const float* x, float* y, int32_t B, int32_t T, const float* mask,
                              int64_t mask_sb, int64_t mask_sh, int64_t mask_sq, int32_t last_row_only, void* workspace,
                              int64_t workspace_bytes, void* stream) {
   MTTS_REQUIRE(enc && enc->layers && x && y && workspace, "null pointer");
   Arena ar(workspace, workspace_bytes);
-  return encoder_forward(enc, x, y, B, T, mask, mask_sb, mask_sh, mask_sq, last_row_only, ar, (cudaStream_t)stream);
+  TcScratch tcs{nullptr, tc_scratch_bytes(enc, (int64_t)B * T), (int64_t)B * T};
+  if (tcs.bytes) tcs.p = ar.take<char>(tcs.bytes);
+  return encoder_forward(enc, x, y, B, T, mask, mask_sb, mask_sh, mask_sq, last_row_only, ar, &tcs,
+                         (cudaStream_t)stream);
+}
+
+int64_t mtts_linear_tc_scratch_bytes(int64_t rows_cap, int32_t K) { return linear_tc_scratch_bytes(rows_cap, K); }
+int mtts_linear_tc_f32(const float* x, int32_t ldx, int64_t M, int32_t K, const void* w_planes, int32_t N,
+                       const float* bias, const float* res, int32_t ldr, float* y, int32_t ldy, int32_t pre_act,
+                       float pre_slope, int32_t post_act, void* scratch, int64_t scratch_bytes, int64_t rows_cap,
+                       void* stream) {
+  return linear_tc(x, ldx, M, K, w_planes, N, bias, res, ldr, y, ldy, pre_act, pre_slope, post_act, 1.0f, scratch,
+                   scratch_bytes, rows_cap, (cudaStream_t)stream);
 }
 
 int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) { return plm_ws_floats(m, B, T) * 4 + 8192; }

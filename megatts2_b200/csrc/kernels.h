@@ -5,6 +5,10 @@
 namespace mtts {
 int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
 int conv1d(const mtts_conv_params& p, cudaStream_t st);   // engine dispatch (FFMA today)
+int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K);
+int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,
+              const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,
+              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, cudaStream_t st);
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
               int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, cudaStream_t st);
 int attention(const mtts_attn_params& p, cudaStream_t st);

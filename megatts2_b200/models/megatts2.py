@@ -99,7 +99,7 @@ class MegaPLM(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def _plan_get(self, device, T):
-        sig = pack.signature(list(self.parameters()))
+        sig = pack.signature(list(self.parameters())) + (getattr(self.plm, "engine", None), pack.default_engine())
         if self._plan is None or self._plan.sig != sig or self._plan.pe_rows < T:
             pl = pack.Plan()
             pl.sig = sig
@@ -176,7 +176,7 @@ class MegaADM(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def _plan_get(self, device, T):
-        sig = pack.signature(list(self.parameters()))
+        sig = pack.signature(list(self.parameters())) + (getattr(self.adm, "engine", None), pack.default_engine())
         if self._plan is None or self._plan.sig != sig or self._plan.pe_rows < T:
             pl = pack.Plan()
             pl.sig = sig

@@ -116,13 +116,15 @@ class TransformerEncoder(pack.PlanMixin, nn.Module):
 def encoder_plan(owner, layers):
     """Packed weights + mtts_encoder struct for a list of layers, cached on `owner`."""
     params = [p for lyr in layers for p in lyr.parameters()]
-    sig = pack.signature(params)
+    engine = getattr(owner, "engine", None)
+    engine = pack.default_engine() if engine is None else int(engine)
+    sig = pack.signature(params) + (engine,)
     pl = owner._plan
     if pl is None or pl.sig != sig:
         pl = pack.Plan()
         pl.sig = sig
         l0 = layers[0]
-        pl.enc = pack.build_encoder_struct(pl, layers, l0.dim, l0.n_heads, l0.ff_dim, l0.conv_ff)
+        pl.enc = pack.build_encoder_struct(pl, layers, l0.dim, l0.n_heads, l0.ff_dim, l0.conv_ff, engine)
         owner._plan = pl
     return pl
 

@@ -85,6 +85,27 @@ def linear(x, w_packed, bias=None, **kw):
     return y.reshape(*shp[:-1], w_packed.shape[2])
 
 
+def linear_tc(x, w_planes, bias=None, *, res=None, pre_act=L.ACT_NONE, pre_slope=0.0, post_act=L.ACT_NONE):
+    """Tensor-core (tcgen05, bf16x3) dense layer: x (..., K) fp32, w_planes (3, N, K) bf16 -> (..., N) fp32."""
+    x = _dev(x, name="x")
+    shp = x.shape
+    x2 = x.reshape(-1, shp[-1])
+    if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
+        x2 = x2.contiguous()
+    M, K = x2.shape
+    _, N, K2 = w_planes.shape
+    assert K2 == K and w_planes.dtype == torch.bfloat16 and w_planes.is_contiguous()
+    y = torch.empty(M, N, dtype=_F32, device=x.device)
+    r2 = res.reshape(M, N) if res is not None else None
+    lib = L.lib()
+    nbytes = lib.mtts_linear_tc_scratch_bytes(M, K)
+    scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+    L.check(lib.mtts_linear_tc_f32(_ptr(x2), x2.stride(0), M, K, _ptr(w_planes), N, _ptr(bias), _ptr(r2),
+                                   r2.stride(0) if r2 is not None else 0, _ptr(y), N, pre_act, pre_slope, post_act,
+                                   _ptr(scratch), nbytes, M, _stream()))
+    return y.reshape(*shp[:-1], N)
+
+
 def layernorm(x, gamma, beta, *, res=None, out=None, eps=1e-5, post_act=L.ACT_NONE, accumulate=False):
     x = _dev(x, name="x")
     Cc = x.shape[-1]

@@ -41,6 +41,24 @@ def pack_conv_transpose(w, bias, stride):
     return wp, bp
 
 
+def pack_tc_planes(w):
+    """(N, K) fp32 weight -> (3, N, K) bf16 planes with w = w1 + w2 + w3 to ~2^-24 (round-to-nearest at
+    every step, the same split the kernels apply to activations)."""
+    w = w.detach().float()
+    p1 = w.to(torch.bfloat16)
+    r1 = w - p1.float()
+    p2 = r1.to(torch.bfloat16)
+    p3 = (r1 - p2.float()).to(torch.bfloat16)
+    return torch.stack([p1, p2, p3], 0).contiguous()
+
+
+def default_engine() -> int:
+    """1 = tcgen05 bf16x3 engine for the large GEMMs (default), 0 = fp32 FFMA engine everywhere
+    (MEGATTS2_ENGINE=tc|ffma).  Both are fp32-grade; ids are bit-identical between them in the tests."""
+    import os
+    return 0 if os.environ.get("MEGATTS2_ENGINE", "tc").lower() in ("ffma", "fp32", "0") else 1
+
+
 def signature(tensors):
     """Cheap change detector for a parameter set (storage address + in-place version)."""
     return tuple((t.data_ptr(), t._version) for t in tensors)
@@ -82,9 +100,15 @@ class Plan:
         return t.data_ptr()
 
 
-def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff):
+def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff, engine=0):
     """layers: iterable of objects with .norm1 .norm2 .attn(w_q,w_k,w_v,out_proj[0]) .ff"""
     arr = (L.EncoderLayer * len(layers))()
+    tc = engine == 1 and not conv_ff
+
+    def tcp(w):
+        t = pack_tc_planes(w)
+        plan.keep.append(t)
+        return t.data_ptr()
     for i, lyr in enumerate(layers):
         a = lyr.attn
         e = arr[i]
@@ -99,9 +123,14 @@ def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff):
         else:
             e.w_ff1, e.b_ff1 = plan.p(pack_linear(lyr.ff[0].weight)), plan.p(lyr.ff[0].bias)
             e.w_ff2, e.b_ff2 = plan.p(pack_linear(lyr.ff[3].weight)), plan.p(lyr.ff[3].bias)
+        if tc:
+            e.w_qkv_tc = tcp(torch.cat([a.w_q.weight.detach(), a.w_k.weight.detach(), a.w_v.weight.detach()], 0))
+            e.w_o_tc = tcp(a.out_proj[0].weight)
+            e.w_ff1_tc, e.w_ff2_tc = tcp(lyr.ff[0].weight), tcp(lyr.ff[3].weight)
     plan.hold(arr)
     enc = L.Encoder()
     enc.n_layers, enc.d_model, enc.n_heads, enc.ff_dim, enc.conv_ff = len(layers), d_model, n_heads, ff_dim, int(conv_ff)
+    enc.engine = 1 if tc else 0
     enc.layers = C.cast(arr, C.POINTER(L.EncoderLayer))
     return enc
 

@@ -130,3 +130,24 @@ def test_reference_loads_oracle_weights_strict():
     G.load_state_dict(weights.g_state_dict(), strict=True)
     plm.load_state_dict(weights.plm_state_dict(), strict=True)
     adm.load_state_dict(weights.adm_state_dict(), strict=True)
+
+
+def test_c_oracle_vq_matches_reference_fixture(golden, weights_cpu):
+    """the plain-C VQ restatement (oracle/vq_argmin.c) against the reference's indices"""
+    import ctypes
+    import subprocess
+    from conftest import ROOT
+    so = os.path.join(ROOT, "oracle", "_build", "libvq_oracle.so")
+    if not os.path.exists(so):
+        os.makedirs(os.path.dirname(so), exist_ok=True)
+        subprocess.check_call(["gcc", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "oracle", "vq_argmin.c")])
+    lib = ctypes.CDLL(so)
+    g = golden("vq_search")
+    x = g["x"].contiguous()
+    embed = weights_cpu("g")["vqpe.vq.vq.layers.0._codebook.embed"].contiguous()
+    idx = torch.empty(x.shape[0], dtype=torch.int64)
+    lib.vq_argmin_oracle(ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(embed.data_ptr()), ctypes.c_int64(x.shape[0]),
+                         ctypes.c_int(256), ctypes.c_int(1024), ctypes.c_void_p(idx.data_ptr()))
+    mism = idx != g["idx"]
+    assert bool((g["gap64"][mism] < 2e-4).all())      # only genuine fp32 near-ties may differ
+    assert torch.equal(idx[:512], g["idx"][:512])
