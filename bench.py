@@ -256,14 +256,31 @@ def run_b200(args):
         gms, gfl, gn = C.c_double(), C.c_double(), C.c_int64()
         L.check(lib.mtts_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn)))
         log(f"roofline leg: {gn.value} tap-GEMM launches, {gms.value:.1f} ms, {gfl.value / 1e12:.2f} TFLOP")
+        sp = (C.c_double * 6)()
+        lib.mtts_profile_split(sp)
         pk, pk_src = peaks()
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
-        achieved = gfl.value / (gms.value / 1e3) / 1e12 if gms.value > 0 else 0.0
-        roofline = {"bound": "tensor", "kernel": "tapconv_kernel (fp32 FFMA tap-GEMM: all Linear/Conv1d/ConvTranspose1d)",
+        step_ms = ms / args.steps
+
+        def cls(ms_, fl_, n_):
+            return {"ms_per_step": round(ms_, 2), "tflop_per_step": round(fl_ / 1e12, 3), "launches_per_step": int(n_),
+                    "achieved_tflops": round(fl_ / (ms_ / 1e3) / 1e12, 2) if ms_ > 0 else 0.0,
+                    "share_of_step": round(ms_ / step_ms, 3)}
+        classes = {"fp32_ffma_tapconv_kernel": cls(sp[0], sp[1], sp[2]),
+                   "tcgen05_bf16x3_gemm_and_conv_kernels (incl. their split kernels)": cls(sp[3], sp[4], sp[5])}
+        dom_tc = sp[3] >= sp[0]
+        d_ms, d_fl = (sp[3], sp[4]) if dom_tc else (sp[0], sp[1])
+        achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
+        roofline = {"bound": "tensor",
+                    "kernel": ("gemm_bf16x3_kernel / conv_bf16x3_kernel (tcgen05 tap-GEMM, 6 bf16 MMAs per fp32-grade product)"
+                               if dom_tc else "tapconv_kernel (fp32 FFMA tap-GEMM)"),
                     "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-                    "traffic": None, "peak_source": f"{pk_src} bf16 dense (sustained); the kernel runs exact fp32 FFMA",
-                    "gemm_ms_per_step": round(gms.value, 2), "gemm_tflop_per_step": round(gfl.value / 1e12, 3),
-                    "gemm_launches_per_step": gn.value, "gemm_share_of_step": round(gms.value / (ms / args.steps), 3)}
+                    "traffic": None,
+                    "peak_source": f"{pk_src} dense bf16 (sustained). achieved = algorithmic fp32-grade FLOPs (2*M*N*K) / CUDA-event "
+                                   "time of the launches; the bf16x3 scheme issues 6 bf16 MMAs per such FLOP pair, so its "
+                                   "ceiling is peak/6",
+                    "frac_of_bf16x3_ceiling": round(achieved / (peak / 6.0), 4) if dom_tc else None,
+                    "classes": classes}
         cpu = None if args.no_cpu_baseline else cpu_baseline(tts, args)
         result = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,

@@ -44,6 +44,8 @@ int64_t mtts_launch_count(void);
  * the summed kernel time, the summed algorithmic FLOPs (2*M*N*Cin*k) and the launch count. */
 int mtts_profile_begin(void);
 int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
+/* per-engine split of the last profile_end: {ffma_ms, ffma_flops, ffma_launches, tc_ms, tc_flops, tc_launches} */
+int mtts_profile_split(double* out6);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };
@@ -75,6 +77,11 @@ typedef struct {
   int64_t out_shift;                       /* 0 for ordinary convs */
   int64_t y_batch_elems;                   /* 0 -> Tout*ldy */
   const int32_t* in_lens;                  /* optional (B): rows >= len read as zero / reflect about len */
+  /* tensor-core engine (optional): the same weights as three bf16 planes (3, k, Cout, Cin) and a scratch
+   * buffer for the padded activation planes (>= 6*B*(Tout + dil*(k-1))*Cin + 2048 bytes).  Used when the
+   * shape is eligible (stride 1, Cin % 8 == 0, Cin >= 32, Cout in {32, 64, >= 128 and % 32 == 0}). */
+  const void* w_tc;
+  void* tc_scratch; int64_t tc_scratch_bytes;
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);
@@ -224,10 +231,11 @@ int mtts_adm_infer_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ConvNet family (modules/convnet.py).  One ConvBlock = ReLU -> Conv1d(C,C,k,same) -> LN(C). */
-typedef struct { const float *w, *b, *ln_g, *ln_b; } mtts_conv_block;   /* w packed (k,C,C) */
+typedef struct { const float *w, *b, *ln_g, *ln_b; const void* w_tc; } mtts_conv_block;   /* w packed (k,C,C); w_tc (3,k,C,C) bf16 or NULL */
 
 typedef struct {
   int32_t in_channels, out_channels, hidden, k, n_stacks, n_blocks;
+  int32_t engine;                      /* 0: fp32 FFMA; 1: tcgen05 bf16x3 for the eligible convs */
   const float *w_first, *b_first;      /* packed (k, Cin, hidden) */
   const float *w_last, *b_last;        /* packed (k, hidden, Cout) */
   const mtts_conv_block* blocks;       /* HOST array [n_stacks*n_blocks] */
@@ -240,6 +248,7 @@ int mtts_convnet_forward_f32(const mtts_convnet* n, const float* x, int64_t x_sb
 
 typedef struct {
   int32_t in_channels, out_channels, hidden, k, n_layers, n_stacks, n_blocks;
+  int32_t engine;
   int32_t middle_kind;                 /* 0: MaxPool1d(middle_k, ceil) ; 1: strided Conv1d(k=middle_k, stride, pad) */
   int32_t middle_k, middle_stride, middle_pad;
   const float *w_middle, *b_middle;    /* packed (middle_k, hidden, hidden) when middle_kind == 1 */
@@ -255,9 +264,13 @@ int mtts_convnet_double_forward_f32(const mtts_convnet_double* n, const float* x
 
 /* HiFi-GAN V1 generator (speechbrain HIFIGAN.decode_batch, called at
  * models/megatts2.py:370-372).  mel (B, T, 80) channels-last -> wav (B, 256*(T+2*pad)). */
-typedef struct { const float *w1[3], *b1[3], *w2[3], *b2[3]; int32_t k; int32_t dil[3]; } mtts_hifigan_resblock;
+typedef struct {
+  const float *w1[3], *b1[3], *w2[3], *b2[3]; int32_t k; int32_t dil[3];
+  const void *w1_tc[3], *w2_tc[3];     /* (3, k, C, C) bf16 planes or NULL */
+} mtts_hifigan_resblock;
 typedef struct {
   int32_t in_channels, ch0, n_ups, n_kernels, inference_padding;
+  int32_t engine;
   int32_t up_factor[4], up_kernel[4];
   const float *w_pre, *b_pre;          /* packed (7, 80, ch0) */
   const float *w_up[4], *b_up[4];      /* packed (2, Cin, s*Cout), bias expanded to (s*Cout) */

@@ -29,6 +29,7 @@ class ConvParams(C.Structure):
         ("out_scale", f32), ("accumulate", i32),
         ("out_shift", i64), ("y_batch_elems", i64),
         ("in_lens", vp),
+        ("w_tc", vp), ("tc_scratch", vp), ("tc_scratch_bytes", i64),
     ]
 
 
@@ -66,30 +67,31 @@ class ADM(C.Structure):
 
 
 class ConvBlock(C.Structure):
-    _fields_ = [("w", vp), ("b", vp), ("ln_g", vp), ("ln_b", vp)]
+    _fields_ = [("w", vp), ("b", vp), ("ln_g", vp), ("ln_b", vp), ("w_tc", vp)]
 
 
 class ConvNet(C.Structure):
     _fields_ = [("in_channels", i32), ("out_channels", i32), ("hidden", i32), ("k", i32), ("n_stacks", i32),
-                ("n_blocks", i32), ("w_first", vp), ("b_first", vp), ("w_last", vp), ("b_last", vp),
+                ("n_blocks", i32), ("engine", i32), ("w_first", vp), ("b_first", vp), ("w_last", vp), ("b_last", vp),
                 ("blocks", C.POINTER(ConvBlock))]
 
 
 class ConvNetDouble(C.Structure):
     _fields_ = [("in_channels", i32), ("out_channels", i32), ("hidden", i32), ("k", i32), ("n_layers", i32),
-                ("n_stacks", i32), ("n_blocks", i32), ("middle_kind", i32), ("middle_k", i32),
+                ("n_stacks", i32), ("n_blocks", i32), ("engine", i32), ("middle_kind", i32), ("middle_k", i32),
                 ("middle_stride", i32), ("middle_pad", i32), ("w_middle", vp), ("b_middle", vp),
                 ("w_first", vp), ("b_first", vp), ("w_last", vp), ("b_last", vp),
                 ("blocks", C.POINTER(ConvBlock))]
 
 
 class HifiganResblock(C.Structure):
-    _fields_ = [("w1", vp * 3), ("b1", vp * 3), ("w2", vp * 3), ("b2", vp * 3), ("k", i32), ("dil", i32 * 3)]
+    _fields_ = [("w1", vp * 3), ("b1", vp * 3), ("w2", vp * 3), ("b2", vp * 3), ("k", i32), ("dil", i32 * 3),
+                ("w1_tc", vp * 3), ("w2_tc", vp * 3)]
 
 
 class Hifigan(C.Structure):
     _fields_ = [("in_channels", i32), ("ch0", i32), ("n_ups", i32), ("n_kernels", i32), ("inference_padding", i32),
-                ("up_factor", i32 * 4), ("up_kernel", i32 * 4), ("w_pre", vp), ("b_pre", vp),
+                ("engine", i32), ("up_factor", i32 * 4), ("up_kernel", i32 * 4), ("w_pre", vp), ("b_pre", vp),
                 ("w_up", vp * 4), ("b_up", vp * 4), ("resblocks", C.POINTER(HifiganResblock)),
                 ("w_post", vp), ("b_post", vp)]
 
@@ -101,6 +103,7 @@ SIGNATURES = {
     "mtts_launch_count": (i64, []),
     "mtts_profile_begin": (C.c_int, []),
     "mtts_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
+    "mtts_profile_split": (C.c_int, [C.POINTER(C.c_double)]),
     "mtts_conv1d_f32": (C.c_int, [C.POINTER(ConvParams), vp]),
     "mtts_linear_tc_scratch_bytes": (i64, [i64, i32]),
     "mtts_linear_tc_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, vp, i64, i64, vp]),

@@ -1,0 +1,389 @@
+// Tensor-core tap-GEMM: stride-1 Conv1d (any kernel size / dilation / padding mode) on tcgen05 with
+// the bf16x3 split of gemm_tc.cu.  Used for the HiFi-GAN ResBlock convs and the ConvBlock stacks
+// (modules/convnet.py:13-18; speechbrain HifiGAN ResBlock1), i.e. wherever Cin % 8 == 0, Cin >= 32 and
+// Cout in {32, 64, >= 128}.
+//
+// Data flow:  fp32 activations (B,T,C) --split_pad--> three bf16 planes (B, T + halo, C) with the
+// padding MATERIALISED (zero / reflect / replicate) and the pre-activation applied, so that the conv
+// becomes a "valid" conv over the planes and tap j of an output tile is simply the same 128-row
+// tile shifted by j*dil rows: one 3-D TMA box load per (tap, channel slab), no im2col, the k-fold
+// re-reads are served by L2.  Weights are packed per tap as (k, Cout, Cin) bf16 planes (K-major B).
+#include <mutex>
+#include <unordered_map>
+
+#include "kernels.h"
+#include "tc_ptx.cuh"
+
+namespace mtts {
+
+struct ConvTcMaps {
+  CUtensorMap a[3];   // 3-D: (C, Tp, B)
+  CUtensorMap b[3];   // 2-D: (Cin, k*Cout)
+};
+
+struct ConvTcArgs {
+  int32_t B, T, Cin, Cout, k, dil;
+  const float* bias;
+  const float* res; int64_t res_sb; int32_t ldr;
+  float* y; int64_t y_sb; int32_t ldy;
+  int32_t post_act; float out_scale; int32_t accumulate;
+};
+
+template <int BN, int SWB>
+struct ConvTcCfg {
+  static constexpr int BK = SWB / 2;                       // bf16 elements per swizzled row
+  static constexpr int A_PLANE = 128 * SWB;
+  static constexpr int B_PLANE = BN * SWB;
+  static constexpr int STAGE = 3 * (A_PLANE + B_PLANE);
+  static constexpr int STAGES_RAW = (224 * 1024) / STAGE;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;   // 2 buffers x (main + correction) x BN
+};
+
+template <int BN, int SWB>
+__global__ void __launch_bounds__(256, 1)
+conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
+  using Cfg = ConvTcCfg<BN, SWB>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bars = smem_base + STAGES * Cfg::STAGE;
+  const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
+  const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
+  const uint32_t tmem_slot = tempty_bar + 16;
+  uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int num_t = (g.T + 127) / 128, num_n = (g.Cout + BN - 1) / BN;
+  const int num_tiles = g.B * num_t * num_n;
+  const int ncb = (g.Cin + Cfg::BK - 1) / Cfg::BK;
+  const int num_k = g.k * ncb;
+
+  if (warp == 0 && lane == 0) {
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[i]) : "memory");
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(full_bar + 8 * s, 1);
+      mbar_init(empty_bar + 8 * s, 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(tfull_bar + 8 * s, 1);
+      mbar_init(tempty_bar + 8 * s, 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    if (lane == 0) {   // ================= TMA producer =================
+      int stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int nb = tile % num_n, r = tile / num_n;
+        const int tb = r % num_t, b = r / num_t;
+        for (int kb = 0; kb < num_k; ++kb) {
+          const int j = kb / ncb, cb = kb - j * ncb;
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t fb = full_bar + 8 * stage;
+          mbar_expect_tx(fb, Cfg::STAGE);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE;
+          const uint32_t sb = sa + 3 * Cfg::A_PLANE;
+#pragma unroll
+          for (int p = 0; p < 3; ++p) {
+            tma_load_3d(sa + p * Cfg::A_PLANE, &maps.a[p], fb, cb * Cfg::BK, tb * 128 + j * g.dil, b);
+            tma_load_2d(sb + p * Cfg::B_PLANE, &maps.b[p], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {   // ================= MMA issuer =================
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+      int stage = 0, phase = 0, it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        const int as = it & 1, aphase = (it >> 1) & 1;
+        mbar_wait(tempty_bar + 8 * as, aphase ^ 1);
+        tc_fence_after();
+        const uint32_t d_main = tmem_base + as * (2 * BN);
+        const uint32_t d_corr = d_main + BN;
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(full_bar + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE;
+          const uint32_t sb = sa + 3 * Cfg::A_PLANE;
+#pragma unroll
+          for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
+            uint64_t ad[3], bd[3];
+#pragma unroll
+            for (int p = 0; p < 3; ++p) {
+              ad[p] = umma_desc_kmajor<SWB>(sa + p * Cfg::A_PLANE + ks * 32);
+              bd[p] = umma_desc_kmajor<SWB>(sb + p * Cfg::B_PLANE + ks * 32);
+            }
+            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
+            tc_mma_bf16(d_corr, ad[1], bd[1], idesc, first);
+            tc_mma_bf16(d_corr, ad[0], bd[2], idesc, 1u);
+            tc_mma_bf16(d_corr, ad[2], bd[0], idesc, 1u);
+            tc_mma_bf16(d_corr, ad[0], bd[1], idesc, 1u);
+            tc_mma_bf16(d_corr, ad[1], bd[0], idesc, 1u);
+            tc_mma_bf16(d_main, ad[0], bd[0], idesc, first);
+          }
+          tc_commit(empty_bar + 8 * stage);
+          if (kb == num_k - 1) tc_commit(tfull_bar + 8 * as);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp >= 4) {
+    // ================= epilogue =================
+    const int q = warp - 4;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+      const int nb = tile % num_n, r0 = tile / num_n;
+      const int tb = r0 % num_t, b = r0 / num_t;
+      const int as = it & 1, aphase = (it >> 1) & 1;
+      mbar_wait(tfull_bar + 8 * as, aphase);
+      tc_fence_after();
+      const int t = tb * 128 + q * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32], rc[32];
+        const uint32_t ta = tmem_base + as * (2 * BN) + c * 32 + ((uint32_t)(q * 32) << 16);
+        tmem_ld32(ta, r);
+        tmem_ld32(ta + BN, rc);
+        const int n0 = nb * BN + c * 32;
+        if (t < g.T && n0 < g.Cout) {
+          float* yr = g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0;
+          const float* rr = g.res ? g.res + (int64_t)b * g.res_sb + (int64_t)t * g.ldr + n0 : nullptr;
+          if (n0 + 32 <= g.Cout) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float v[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                float x = __uint_as_float(r[j + e]) + __uint_as_float(rc[j + e]);
+                if (g.bias) x += __ldg(g.bias + n0 + j + e);
+                v[e] = act_apply(x, g.post_act, 0.f);
+              }
+              if (rr) {
+                const float4 tt = *reinterpret_cast<const float4*>(rr + j);
+                v[0] += tt.x; v[1] += tt.y; v[2] += tt.z; v[3] += tt.w;
+              }
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] *= g.out_scale;
+              if (g.accumulate) {
+                const float4 o = *reinterpret_cast<const float4*>(yr + j);
+                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
+              }
+              *reinterpret_cast<float4*>(yr + j) = make_float4(v[0], v[1], v[2], v[3]);
+            }
+          } else {
+            for (int j = 0; j < 32 && n0 + j < g.Cout; ++j) {
+              float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+              if (g.bias) x += __ldg(g.bias + n0 + j);
+              x = act_apply(x, g.post_act, 0.f);
+              if (rr) x += rr[j];
+              x *= g.out_scale;
+              if (g.accumulate) x += yr[j];
+              yr[j] = x;
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// fp32 (B,T,C) -> three bf16 planes (B, Tp = T + hl + hr, C): padding materialised, pre-activation applied
+__global__ void __launch_bounds__(256)
+split_pad_bf16x3_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int C, int hl, int Tp, int pad_mode,
+                        int pre_act, float slope, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
+                        int64_t total4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int cq = C >> 2;
+  const int c = (int)(i % cq) * 4;
+  const int64_t bu = i / cq;
+  const int u = (int)(bu % Tp);
+  const int b = (int)(bu / Tp);
+  int ti = u - hl;
+  if (ti < 0 || ti >= T) {
+    if (pad_mode == MTTS_PAD_ZERO) ti = -1;
+    else if (pad_mode == MTTS_PAD_REPLICATE) ti = ti < 0 ? 0 : T - 1;
+    else {
+      if (ti < 0) ti = -ti;
+      if (ti >= T) ti = 2 * (T - 1) - ti;
+      if (ti < 0 || ti >= T) ti = -1;
+    }
+  }
+  float f[4] = {0.f, 0.f, 0.f, 0.f};
+  if (ti >= 0) {
+    const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)b * x_sb + (int64_t)ti * ldx + c);
+    f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
+  }
+  __nv_bfloat16 p[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a = act_apply(f[e], pre_act, slope);
+    p[0][e] = __float2bfloat16_rn(a);
+    a -= __bfloat162float(p[0][e]);
+    p[1][e] = __float2bfloat16_rn(a);
+    a -= __bfloat162float(p[1][e]);
+    p[2][e] = __float2bfloat16_rn(a);
+  }
+  const int64_t off = ((int64_t)b * Tp + u) * C + c;
+#pragma unroll
+  for (int qn = 0; qn < 3; ++qn) {
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(p[qn][0]) | ((uint32_t)__bfloat16_as_ushort(p[qn][1]) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(p[qn][2]) | ((uint32_t)__bfloat16_as_ushort(p[qn][3]) << 16);
+    *reinterpret_cast<uint2*>(planes + qn * plane_stride + off) = o;
+  }
+}
+
+// ------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn g_enc = nullptr;
+static std::mutex g_ctc_mu;
+static int g_ctc_sms = 0;
+
+struct CMapKey {
+  const void* p; uint64_t d0, d1, d2, b0, b1; int swb;
+  bool operator==(const CMapKey& o) const {
+    return p == o.p && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && swb == o.swb;
+  }
+};
+struct CMapKeyHash {
+  size_t operator()(const CMapKey& k) const {
+    uint64_t h = (uint64_t)k.p;
+    h = h * 0x9E3779B97F4A7C15ull + k.d0; h = h * 0x9E3779B97F4A7C15ull + k.d1; h = h * 0x9E3779B97F4A7C15ull + k.d2;
+    h = h * 0x9E3779B97F4A7C15ull + k.b0 * 131 + k.b1 * 7 + k.swb;
+    return (size_t)h;
+  }
+};
+static std::unordered_map<CMapKey, CUtensorMap, CMapKeyHash> g_cmaps;
+
+static int ctc_init() {
+  if (g_enc) return 0;
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
+    return fail(MTTS_ERR_CUDA, "%s: cuTensorMapEncodeTiled not available", "conv_tc");
+  g_enc = (EncodeTiledFn)fn;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&g_ctc_sms, cudaDevAttrMultiProcessorCount, dev);
+  return 0;
+}
+
+// bf16 tensor (d2, d1, d0) row-major, box (1, b1, b0), SWB-byte swizzle; rank 2 when d2 == 0
+static int cmap_get(const void* p, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, int swb,
+                    CUtensorMap* out) {
+  CMapKey key{p, d0, d1, d2, b0, b1, swb};
+  auto itf = g_cmaps.find(key);
+  if (itf != g_cmaps.end()) { *out = itf->second; return 0; }
+  const int rank = d2 ? 3 : 2;
+  cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
+  cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
+  cuuint32_t box[3] = {b0, b1, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  CUtensorMap m;
+  CUresult r = g_enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(p), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(MTTS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed: %lld", "conv_tc", (long long)r);
+  if (g_cmaps.size() > 8192) g_cmaps.clear();
+  g_cmaps[key] = m;
+  *out = m;
+  return 0;
+}
+
+template <int BN, int SWB>
+static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStream_t st) {
+  using Cfg = ConvTcCfg<BN, SWB>;
+  static bool attr = false;
+  if (!attr) {
+    cudaError_t e = cudaFuncSetAttribute(conv_bf16x3_kernel<BN, SWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "conv_tc", (long long)e);
+    attr = true;
+  }
+  const int64_t tiles = (int64_t)a.B * cdiv64(a.T, 128) * cdiv64(a.Cout, BN);
+  const int grid = (int)(tiles < g_ctc_sms ? tiles : g_ctc_sms);
+  conv_bf16x3_kernel<BN, SWB><<<grid, 256, Cfg::SMEM, st>>>(maps, a);
+  MTTS_CHECK_LAUNCH();
+  return 0;
+}
+
+bool conv_tc_eligible(const mtts_conv_params& p) {
+  if (!p.w_tc || !p.tc_scratch) return false;
+  if (p.stride != 1 || p.out_shift != 0 || p.in_lens) return false;
+  if (p.Cin % 8 != 0 || p.Cin < 32 || p.ldx % 4 != 0 || (p.x_batch_stride % 4) != 0) return false;
+  if (!(p.Cout == 32 || p.Cout == 64 || (p.Cout >= 128 && p.Cout % 32 == 0))) return false;
+  if (p.Cin < 64 && p.Cout != 32) return false;          // the SWB=64 variant is instantiated for BN=32 only
+  if (p.ldy % 4 != 0 || p.y_batch_stride % 4 != 0 || (((uintptr_t)p.y) & 15) != 0) return false;
+  if (p.res && (p.ldr % 4 != 0 || p.res_batch_stride % 4 != 0 || (((uintptr_t)p.res) & 15) != 0)) return false;
+  if ((((uintptr_t)p.x) & 15) != 0) return false;
+  if (p.Tout != p.Tin + 2 * p.pad - p.dil * (p.k - 1)) return false;
+  if ((int64_t)p.B * p.Tout < 128) return false;         // tiny problems stay on the exact FFMA engine
+  const int Tp = p.Tout + p.dil * (p.k - 1);
+  return 3 * (int64_t)p.B * Tp * p.Cin * 2 + 2048 <= p.tc_scratch_bytes;
+}
+
+int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ctc_mu);
+  MTTS_TRY(ctc_init());
+  const int halo = p.dil * (p.k - 1);
+  const int hl = p.pad, Tp = p.Tout + halo;
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
+  const int64_t plane_stride = (int64_t)p.B * Tp * p.Cin;
+  {
+    const int64_t total4 = plane_stride / 4;
+    split_pad_bf16x3_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
+                                                                          p.pad_mode, p.pre_act, p.pre_slope, planes,
+                                                                          plane_stride, total4);
+    MTTS_CHECK_LAUNCH();
+  }
+  const int BN = p.Cout >= 128 ? 128 : p.Cout;
+  const int SWB = p.Cin >= 64 ? 128 : 64;
+  ConvTcMaps maps;
+  for (int q = 0; q < 3; ++q) {
+    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp, (uint64_t)p.B, SWB / 2, 128, SWB, &maps.a[q]));
+    MTTS_TRY(cmap_get((const __nv_bfloat16*)p.w_tc + (int64_t)q * p.k * p.Cout * p.Cin, (uint64_t)p.Cin,
+                      (uint64_t)p.k * p.Cout, 0, SWB / 2, BN, SWB, &maps.b[q]));
+  }
+  ConvTcArgs a;
+  a.B = p.B; a.T = p.Tout; a.Cin = p.Cin; a.Cout = p.Cout; a.k = p.k; a.dil = p.dil;
+  a.bias = p.bias; a.res = p.res; a.res_sb = p.res_batch_stride; a.ldr = p.ldr;
+  a.y = p.y; a.y_sb = p.y_batch_stride; a.ldy = p.ldy;
+  a.post_act = p.post_act; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
+  if (BN == 128) return conv_tc_launch<128, 128>(maps, a, st);
+  if (BN == 64) return conv_tc_launch<64, 128>(maps, a, st);
+  if (SWB == 128) return conv_tc_launch<32, 128>(maps, a, st);
+  return conv_tc_launch<32, 64>(maps, a, st);
+}
+
+}  // namespace mtts

@@ -9,33 +9,45 @@ namespace mtts {
 
 // Optional per-launch timing of the tap-GEMM kernels (bench.py's roofline leg): CUDA events on
 // the launching stream around every conv1d launch; off by default, never on the timed path.
-struct ProfRec { cudaEvent_t a, b; double flops; };
+struct ProfRec { cudaEvent_t a, b; double flops; bool tc = false; };
 static std::mutex g_prof_mu;
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 
 int conv1d(const mtts_conv_params& p, cudaStream_t st) {
-  if (!g_prof_on) return conv1d_ffma(p, st);
+  const bool tc = conv_tc_eligible(p);
+  if (!g_prof_on) return tc ? conv_tc(p, st) : conv1d_ffma(p, st);
   std::lock_guard<std::mutex> lk(g_prof_mu);
   ProfRec r;
   if (cudaEventCreate(&r.a) != cudaSuccess || cudaEventCreate(&r.b) != cudaSuccess)
     return fail(MTTS_ERR_CUDA, "%s: cudaEventCreate failed", "profile");
   r.flops = 2.0 * (double)p.B * p.Tout * p.Cout * p.Cin * p.k;
+  r.tc = tc;
   cudaEventRecord(r.a, st);
-  const int rc = conv1d_ffma(p, st);
+  const int rc = tc ? conv_tc(p, st) : conv1d_ffma(p, st);
   cudaEventRecord(r.b, st);
   g_prof.push_back(r);
   return rc;
 }
+
+// tensor-core context of a composite driver call: engine switch + scratch for activation planes
+struct ConvTc { int engine; void* scratch; int64_t bytes; };
+static inline void attach_tc(mtts_conv_params& p, const void* w_tc, const ConvTc* tc) {
+  if (tc && tc->engine == 1 && w_tc && tc->scratch) {
+    p.w_tc = w_tc; p.tc_scratch = tc->scratch; p.tc_scratch_bytes = tc->bytes;
+  }
+}
+static inline int64_t conv_tc_scratch_need(int64_t B, int64_t Tp, int64_t C) { return 6 * B * Tp * C + 4096; }
 
 // scratch for the tensor-core engine's activation planes, carved once per driver call so that the
 // (cached) TMA descriptors keep hitting across the steps of an autoregressive loop
 struct TcScratch { void* p; int64_t bytes; int64_t rows_cap; };
 
 static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
-  if (e->engine != 1 || e->conv_ff) return 0;
+  if (e->engine != 1) return 0;
   const int kmax = e->ff_dim > e->d_model ? e->ff_dim : e->d_model;
-  return linear_tc_scratch_bytes(rows_cap, kmax) + 1024;
+  // conv-FF (k = 5): padded planes need 4 halo rows per sequence; rows_cap + 4*rows_cap covers any batch split
+  return linear_tc_scratch_bytes(e->conv_ff ? 5 * rows_cap + 64 : rows_cap, kmax) + 4096;
 }
 
 // dense layer dispatch: tcgen05 bf16x3 when enabled, packed planes exist and the tile is worth it
@@ -48,6 +60,7 @@ static int lin(const mtts_encoder* e, const TcScratch* tc, const float* x, int l
     if (prof) {
       cudaEventCreate(&r.a); cudaEventCreate(&r.b);
       r.flops = 2.0 * (double)M * N * K;
+      r.tc = true;
       cudaEventRecord(r.a, st);
     }
     const int rc = linear_tc(x, ldx, M, K, wtc, N, bias, res, ldr, y, ldy, 0, 0.f, post_act, 1.0f, tc->p, tc->bytes,
@@ -110,11 +123,14 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       if (e->conv_ff) {
         // x = LN2(x); x = x + conv5(relu(conv5(x)))       (transformer.py:96-98)
         MTTS_TRY(layernorm(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, xw, D, M, D, 1e-5f, 0, 0, st));
+        ConvTc ctc{e->engine, tc ? tc->p : nullptr, tc ? tc->bytes : 0};
         mtts_conv_params c1 = conv_same_params(xw, L.w_ff1, L.b_ff1, f, B, T, D, F, 5, 1, MTTS_PAD_ZERO);
         c1.post_act = MTTS_ACT_RELU;
+        attach_tc(c1, L.w_ff1_tc, &ctc);
         MTTS_TRY(conv1d(c1, st));
         mtts_conv_params c2 = conv_same_params(f, L.w_ff2, L.b_ff2, xw, B, T, F, D, 5, 1, MTTS_PAD_ZERO);
         c2.res = xw; c2.res_batch_stride = (int64_t)T * D; c2.ldr = D;
+        attach_tc(c2, L.w_ff2_tc, &ctc);
         MTTS_TRY(conv1d(c2, st));
       } else {
         // x = x + W2 relu(W1 LN2(x) + b1) + b2             (transformer.py:101)
@@ -254,7 +270,7 @@ struct StackBufs { float *tmp, *h1; };
 // given, the LAST stack writes (x + y) there instead (optionally accumulating).
 static int residual_stack(const mtts_conv_block* blocks, int n_stacks, int n_blocks, int C, int k, int B, int T,
                           const float* src, float* dst, float* final_dst, int final_accumulate, const StackBufs& sb,
-                          cudaStream_t st) {
+                          const ConvTc* tc, cudaStream_t st) {
   const int64_t M = (int64_t)B * T;
   const float* cur = src;
   for (int s = 0; s < n_stacks; ++s) {
@@ -264,6 +280,7 @@ static int residual_stack(const mtts_conv_block* blocks, int n_stacks, int n_blo
       // ConvBlock (convnet.py:22-31): ReLU -> conv -> LN
       mtts_conv_params p = conv_same_params(yin, bl.w, bl.b, sb.tmp, B, T, C, C, k, 1, MTTS_PAD_ZERO);
       p.pre_act = MTTS_ACT_RELU;
+      attach_tc(p, bl.w_tc, tc);
       MTTS_TRY(conv1d(p, st));
       if (b + 1 < n_blocks) {
         MTTS_TRY(layernorm(sb.tmp, C, bl.ln_g, bl.ln_b, nullptr, 0, sb.h1, C, M, C, 1e-5f, 0, 0, st));
@@ -280,7 +297,7 @@ static int residual_stack(const mtts_conv_block* blocks, int n_stacks, int n_blo
 }
 
 static int64_t convnet_ws_floats(const mtts_convnet* n, int B, int T) {
-  return 3 * ((int64_t)B * T * n->hidden + 64);
+  return 3 * ((int64_t)B * T * n->hidden + 64) + (n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
 }
 
 static int convnet_forward(const mtts_convnet* n, const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb,
@@ -293,11 +310,13 @@ static int convnet_forward(const mtts_convnet* n, const float* x, int64_t x_sb, 
   StackBufs sb;
   sb.tmp = ar.take<float>(M * n->hidden);
   sb.h1 = ar.take<float>(M * n->hidden);
+  ConvTc tc{n->engine, nullptr, n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) : 0};
+  if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet", ar.off);
   mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, xc, B, T, n->in_channels, n->hidden, n->k, 1, MTTS_PAD_ZERO);
   p.ldx = ldx; p.x_batch_stride = x_sb;
   MTTS_TRY(conv1d(p, st));
-  MTTS_TRY(residual_stack(n->blocks, n->n_stacks, n->n_blocks, n->hidden, n->k, B, T, xc, xc, nullptr, 0, sb, st));
+  MTTS_TRY(residual_stack(n->blocks, n->n_stacks, n->n_blocks, n->hidden, n->k, B, T, xc, xc, nullptr, 0, sb, &tc, st));
   mtts_conv_params q = conv_same_params(xc, n->w_last, n->b_last, y, B, T, n->hidden, n->out_channels, n->k, 1, MTTS_PAD_ZERO);
   q.ldy = ldy; q.y_batch_stride = y_sb;
   MTTS_TRY(conv1d(q, st));
@@ -311,7 +330,8 @@ static int cnd_mid_len(const mtts_convnet_double* n, int T) {
 
 static int64_t convnet_double_ws_floats(const mtts_convnet_double* n, int B, int T) {
   const int Tm = cnd_mid_len(n, T);
-  return 4 * ((int64_t)B * T * n->hidden + 64) + 2 * ((int64_t)B * Tm * n->hidden + 64);
+  return 4 * ((int64_t)B * T * n->hidden + 64) + 2 * ((int64_t)B * Tm * n->hidden + 64) +
+         (n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
 }
 
 static int convnet_double_forward(const mtts_convnet_double* n, const float* x, int64_t x_sb, int ldx, float* y,
@@ -329,6 +349,8 @@ static int convnet_double_forward(const mtts_convnet_double* n, const float* x, 
   sb.h1 = ar.take<float>(M * H);
   float* xm = ar.take<float>(Mm * H);
   float* acc = ar.take<float>(Mm * H);
+  ConvTc tc{n->engine, nullptr, n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, H) : 0};
+  if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet_double", ar.off);
   mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, h0, B, T, n->in_channels, H, n->k, 1, MTTS_PAD_ZERO);
   p.ldx = ldx; p.x_batch_stride = x_sb;
@@ -338,7 +360,7 @@ static int convnet_double_forward(const mtts_convnet_double* n, const float* x, 
     const mtts_conv_block* b1 = n->blocks + (int64_t)(l * 2 + 0) * per;
     const mtts_conv_block* b2 = n->blocks + (int64_t)(l * 2 + 1) * per;
     // every layer consumes the SAME first_layer output (convnet.py:205-207)
-    MTTS_TRY(residual_stack(b1, n->n_stacks, n->n_blocks, H, n->k, B, T, h0, xc, nullptr, 0, sb, st));
+    MTTS_TRY(residual_stack(b1, n->n_stacks, n->n_blocks, H, n->k, B, T, h0, xc, nullptr, 0, sb, &tc, st));
     if (n->middle_kind == 0) {
       MTTS_TRY(maxpool_time(xc, (int64_t)T * H, H, xm, (int64_t)Tm * H, H, B, T, H, n->middle_k, st));
     } else {
@@ -351,7 +373,7 @@ static int convnet_double_forward(const mtts_convnet_double* n, const float* x, 
       m.k = n->middle_k; m.stride = n->middle_stride; m.dil = 1; m.pad = n->middle_pad; m.out_scale = 1.0f;
       MTTS_TRY(conv1d(m, st));
     }
-    MTTS_TRY(residual_stack(b2, n->n_stacks, n->n_blocks, H, n->k, B, Tm, xm, xm, acc, l > 0 ? 1 : 0, sb, st));
+    MTTS_TRY(residual_stack(b2, n->n_stacks, n->n_blocks, H, n->k, B, Tm, xm, xm, acc, l > 0 ? 1 : 0, sb, &tc, st));
   }
   mtts_conv_params q = conv_same_params(acc, n->w_last, n->b_last, y, B, Tm, H, n->out_channels, n->k, 1, MTTS_PAD_ZERO);
   q.ldy = ldy; q.y_batch_stride = y_sb;
@@ -369,7 +391,8 @@ static int64_t hifigan_ws_floats(const mtts_hifigan* h, int B, int T) {
     C /= 2;
     if (L * C > big) big = L * C;
   }
-  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64);
+  const int64_t tcb = h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0;   // + halo rows
+  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + tcb / 4 + 64;
 }
 
 static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int mel_ld, int B, int T, float* wav,
@@ -389,6 +412,8 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
   float* mp = ar.take<float>((int64_t)B * Tp * h->in_channels);
   float* bufs[5];
   for (int i = 0; i < 5; ++i) bufs[i] = ar.take<float>((int64_t)B * big);
+  ConvTc tc{h->engine, nullptr, h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0};
+  if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "hifigan", ar.off);
   // replicate-pad `pad` frames at both ends (HifiganGenerator.inference)
   MTTS_TRY(copy_strided(mel, mel_sb, mel_ld, 1, mp, (int64_t)Tp * h->in_channels, h->in_channels, 1, B, T,
@@ -427,6 +452,7 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
       for (int m = 0; m < 3; ++m) {
         mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], xt, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);
         c1.pre_act = MTTS_ACT_LEAKY; c1.pre_slope = 0.1f;
+        attach_tc(c1, rb.w1_tc[m], &tc);
         MTTS_TRY(conv1d(c1, st));
         const bool lastm = (m == 2);
         mtts_conv_params c2 = conv_same_params(xt, rb.w2[m], rb.b2[m], lastm ? z : xr, B, Lo, Co, Co, rb.k, 1, MTTS_PAD_REFLECT);
@@ -436,6 +462,7 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
           c2.out_scale = 1.0f / (float)h->n_kernels;
           c2.accumulate = (j > 0);
         }
+        attach_tc(c2, rb.w2_tc[m], &tc);
         MTTS_TRY(conv1d(c2, st));
         xcur = xr;
       }
@@ -461,6 +488,12 @@ using namespace mtts;
 
 extern "C" {
 
+static double g_last_split[6] = {0, 0, 0, 0, 0, 0};
+/* {ffma_ms, ffma_flops, ffma_launches, tc_ms, tc_flops, tc_launches} of the last profile_end */
+int mtts_profile_split(double* out6) {
+  for (int i = 0; i < 6; ++i) out6[i] = g_last_split[i];
+  return 0;
+}
 int mtts_profile_begin(void) {
   std::lock_guard<std::mutex> lk(g_prof_mu);
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
@@ -482,6 +515,13 @@ int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches
   if (gemm_ms) *gemm_ms = ms;
   if (gemm_flops) *gemm_flops = fl;
   if (gemm_launches) *gemm_launches = (int64_t)g_prof.size();
+  g_last_split[0] = g_last_split[1] = g_last_split[2] = g_last_split[3] = g_last_split[4] = g_last_split[5] = 0.0;
+  for (auto& r : g_prof) {
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.a, r.b);
+    const int o = r.tc ? 3 : 0;
+    g_last_split[o] += t; g_last_split[o + 1] += r.flops; g_last_split[o + 2] += 1.0;
+  }
   for (auto& r : g_prof) { cudaEventDestroy(r.a); cudaEventDestroy(r.b); }
   g_prof.clear();
   return 0;

@@ -272,12 +272,15 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def _plan_get(self):
-        sig = pack.signature(list(self.parameters()))
+        engine = getattr(self, "engine", None)
+        engine = pack.default_engine() if engine is None else int(engine)
+        sig = pack.signature(list(self.parameters())) + (engine,)
         if self._plan is None or self._plan.sig != sig:
             c = self.cfg
             pl = pack.Plan()
             pl.sig = sig
             s = L.Hifigan()
+            s.engine = engine
             s.in_channels, s.ch0 = c["in_channels"], c["upsample_initial_channel"]
             s.n_ups, s.n_kernels = len(c["upsample_factors"]), len(c["resblock_kernel_sizes"])
             s.inference_padding = c["inference_padding"]
@@ -295,6 +298,10 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
                     arr[n].dil[m] = c["resblock_dilation_sizes"][j][m]
                     arr[n].w1[m], arr[n].b1[m] = pl.p(pack.pack_conv(rb.convs1[m].weight)), pl.p(rb.convs1[m].bias)
                     arr[n].w2[m], arr[n].b2[m] = pl.p(pack.pack_conv(rb.convs2[m].weight)), pl.p(rb.convs2[m].bias)
+                    if engine == 1:
+                        t1, t2 = pack.pack_conv_tc_planes(rb.convs1[m].weight), pack.pack_conv_tc_planes(rb.convs2[m].weight)
+                        pl.keep += [t1, t2]
+                        arr[n].w1_tc[m], arr[n].w2_tc[m] = t1.data_ptr(), t2.data_ptr()
             pl.hold(arr)
             s.resblocks = C.cast(arr, C.POINTER(L.HifiganResblock))
             s.w_post, s.b_post = pl.p(pack.pack_conv(self.conv_post.weight)), pl.p(self.conv_post.bias)

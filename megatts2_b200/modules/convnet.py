@@ -98,16 +98,19 @@ class ConvNet(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def _plan_get(self):
-        sig = pack.signature(list(self.parameters()))
+        engine = getattr(self, "engine", None)
+        engine = pack.default_engine() if engine is None else int(engine)
+        sig = pack.signature(list(self.parameters())) + (engine,)
         if self._plan is None or self._plan.sig != sig:
             pl = pack.Plan()
             pl.sig = sig
             cin, cout, hid, k, ns, nb = self.cfg
             arr = (L.ConvBlock * (ns * nb))()
-            pack.fill_conv_blocks(pl, arr, 0, self.conv_stack)
+            pack.fill_conv_blocks(pl, arr, 0, self.conv_stack, engine)
             pl.hold(arr)
             s = L.ConvNet()
             s.in_channels, s.out_channels, s.hidden, s.k, s.n_stacks, s.n_blocks = cin, cout, hid, k, ns, nb
+            s.engine = engine
             s.w_first, s.b_first = pl.p(pack.pack_conv(self.first_layer.weight)), pl.p(self.first_layer.bias)
             s.w_last, s.b_last = pl.p(pack.pack_conv(self.last_layer.weight)), pl.p(self.last_layer.bias)
             s.blocks = C.cast(arr, C.POINTER(L.ConvBlock))
@@ -188,7 +191,9 @@ class ConvNetDouble(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def _plan_get(self):
-        sig = pack.signature(list(self.parameters()))
+        engine = getattr(self, "engine", None)
+        engine = pack.default_engine() if engine is None else int(engine)
+        sig = pack.signature(list(self.parameters())) + (engine,)
         if self._plan is None or self._plan.sig != sig:
             pl = pack.Plan()
             pl.sig = sig
@@ -196,11 +201,12 @@ class ConvNetDouble(pack.PlanMixin, nn.Module):
             arr = (L.ConvBlock * (nl * 2 * ns * nb))()
             i = 0
             for lyr in self.layers:
-                i = pack.fill_conv_blocks(pl, arr, i, lyr.conv_stack1)
-                i = pack.fill_conv_blocks(pl, arr, i, lyr.conv_stack2)
+                i = pack.fill_conv_blocks(pl, arr, i, lyr.conv_stack1, engine)
+                i = pack.fill_conv_blocks(pl, arr, i, lyr.conv_stack2, engine)
             pl.hold(arr)
             s = L.ConvNetDouble()
             s.in_channels, s.out_channels, s.hidden, s.k = cin, cout, hid, k
+            s.engine = engine
             s.n_layers, s.n_stacks, s.n_blocks = nl, ns, nb
             mid = self.layers[0].middle_layer
             s.middle_kind, s.middle_k, s.middle_stride, s.middle_pad = _middle_desc(mid)

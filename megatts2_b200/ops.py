@@ -48,8 +48,9 @@ def empty(*shape, dtype=_F32, device=None):
 # ------------------------------------------------------------------------------ tap-GEMM
 def conv1d(x, w_packed, bias=None, *, k, stride=1, dil=1, pad=0, pad_mode=L.PAD_ZERO, pre_act=L.ACT_NONE,
            pre_slope=0.0, post_act=L.ACT_NONE, post_slope=0.0, res=None, out=None, out_scale=1.0, accumulate=False,
-           t_out=None, in_lens=None):
-    """x (B,T,Cin) channels-last, w_packed (k,Cin,Cout) -> (B,T_out,Cout)."""
+           t_out=None, in_lens=None, w_tc=None):
+    """x (B,T,Cin) channels-last, w_packed (k,Cin,Cout) -> (B,T_out,Cout).
+    w_tc: optional (3,k,Cout,Cin) bf16 planes -> the tcgen05 engine is used when the shape is eligible."""
     x = _dev(x, name="x")
     x, x_sb, ldx = _rows(x)
     B, Tin, Cin = x.shape
@@ -74,6 +75,11 @@ def conv1d(x, w_packed, bias=None, *, k, stride=1, dil=1, pad=0, pad_mode=L.PAD_
     p.pre_act, p.pre_slope, p.post_act, p.post_slope = pre_act, pre_slope, post_act, post_slope
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     p.in_lens = _dev(in_lens, torch.int32, "in_lens").data_ptr() if in_lens is not None else None
+    if w_tc is not None:
+        assert w_tc.dtype == torch.bfloat16 and w_tc.is_contiguous() and tuple(w_tc.shape) == (3, k, Cout, Cin)
+        nbytes = 6 * B * (t_out + dil * (k - 1)) * Cin + 4096
+        scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
+        p.w_tc, p.tc_scratch, p.tc_scratch_bytes = w_tc.data_ptr(), scratch.data_ptr(), nbytes
     L.check(L.lib().mtts_conv1d_f32(C.byref(p), _stream()))
     return out
 

@@ -52,6 +52,12 @@ def pack_tc_planes(w):
     return torch.stack([p1, p2, p3], 0).contiguous()
 
 
+def pack_conv_tc_planes(w):
+    """nn.Conv1d weight (Cout, Cin, k) fp32 -> (3, k, Cout, Cin) bf16 planes (per-tap K-major B operands)."""
+    return pack_tc_planes(w.detach().permute(2, 0, 1).contiguous().reshape(-1, w.shape[1])).reshape(
+        3, w.shape[2], w.shape[0], w.shape[1]).contiguous()
+
+
 def default_engine() -> int:
     """1 = tcgen05 bf16x3 engine for the large GEMMs (default), 0 = fp32 FFMA engine everywhere
     (MEGATTS2_ENGINE=tc|ffma).  Both are fp32-grade; ids are bit-identical between them in the tests."""
@@ -103,7 +109,12 @@ class Plan:
 def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff, engine=0):
     """layers: iterable of objects with .norm1 .norm2 .attn(w_q,w_k,w_v,out_proj[0]) .ff"""
     arr = (L.EncoderLayer * len(layers))()
-    tc = engine == 1 and not conv_ff
+    tc = engine == 1
+
+    def tcc(w):
+        t = pack_conv_tc_planes(w)
+        plan.keep.append(t)
+        return t.data_ptr()
 
     def tcp(w):
         t = pack_tc_planes(w)
@@ -126,7 +137,10 @@ def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff, engine
         if tc:
             e.w_qkv_tc = tcp(torch.cat([a.w_q.weight.detach(), a.w_k.weight.detach(), a.w_v.weight.detach()], 0))
             e.w_o_tc = tcp(a.out_proj[0].weight)
-            e.w_ff1_tc, e.w_ff2_tc = tcp(lyr.ff[0].weight), tcp(lyr.ff[3].weight)
+            if conv_ff:
+                e.w_ff1_tc, e.w_ff2_tc = tcc(lyr.ff[0].weight), tcc(lyr.ff[2].weight)
+            else:
+                e.w_ff1_tc, e.w_ff2_tc = tcp(lyr.ff[0].weight), tcp(lyr.ff[3].weight)
     plan.hold(arr)
     enc = L.Encoder()
     enc.n_layers, enc.d_model, enc.n_heads, enc.ff_dim, enc.conv_ff = len(layers), d_model, n_heads, ff_dim, int(conv_ff)
@@ -135,12 +149,16 @@ def build_encoder_struct(plan, layers, d_model, n_heads, ff_dim, conv_ff, engine
     return enc
 
 
-def fill_conv_blocks(plan, arr, offset, stack):
+def fill_conv_blocks(plan, arr, offset, stack, engine=0):
     """stack: ResidualBlockStack; writes n_stacks*n_blocks mtts_conv_block entries at arr[offset:]."""
     i = offset
     for cs in stack.conv_stacks:
         for blk in cs.blocks:
             arr[i].w, arr[i].b = plan.p(pack_conv(blk.conv.weight)), plan.p(blk.conv.bias)
             arr[i].ln_g, arr[i].ln_b = plan.p(blk.norm.weight), plan.p(blk.norm.bias)
+            if engine == 1:
+                t = pack_conv_tc_planes(blk.conv.weight)
+                plan.keep.append(t)
+                arr[i].w_tc = t.data_ptr()
             i += 1
     return i

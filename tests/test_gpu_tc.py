@@ -88,3 +88,96 @@ def test_encoder_tc_vs_ffma(weights_cpu):
     assert (y0 - y1).abs().max().item() < 5e-4
     l1 = run_encoder(plm.plm, list(plm.plm.layers), x, last_row_only=True)
     assert (l1[:, 0] - y0[:, -1]).abs().max().item() < 5e-4
+
+
+# ------------------------------------------------------------------ tensor-core convolution engine
+CONV_TC_CASES = [
+    dict(B=2, T=500, Cin=512, Cout=512, k=3, pre=1),                                   # MRTE ConvBlock
+    dict(B=2, T=300, Cin=384, Cout=384, k=5, pre=1),                                   # VQPE ConvBlock (Cin % 64 == 0)
+    dict(B=2, T=1000, Cin=256, Cout=256, k=11, dil=5, pad_mode=1, pre=2, res=True),    # HiFi-GAN stage 1
+    dict(B=3, T=777, Cin=128, Cout=128, k=3, dil=3, pad_mode=1, pre=2),                # stage 2, ragged tile
+    dict(B=2, T=2000, Cin=64, Cout=64, k=7, dil=3, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),   # BN = 64
+    dict(B=2, T=3000, Cin=32, Cout=32, k=3, pad_mode=1, pre=2),                        # BN = 32, 64-byte swizzle
+    dict(B=2, T=1500, Cin=32, Cout=32, k=11, dil=1, pad_mode=1, pre=2, res=True),
+    dict(B=2, T=64, Cin=512, Cout=1024, k=5, post=1),                                  # conv-FF first conv
+    dict(B=2, T=64, Cin=1024, Cout=512, k=5, res=True),                                # conv-FF second conv
+    dict(B=1, T=130, Cin=96, Cout=160, k=3, pad_mode=2),                               # odd sizes: K and N tails
+]
+
+
+@pytest.mark.parametrize("case", CONV_TC_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
+def test_conv_tc_vs_fp64(case):
+    import torch.nn.functional as F
+    from megatts2_b200 import ops
+    c = dict(dil=1, pad_mode=0, pre=0, post=0, res=False, acc=False, scale=1.0)
+    c.update(case)
+    k, dil = c["k"], c["dil"]
+    pad = dil * (k - 1) // 2
+    g = gen(sum(v if isinstance(v, int) else 1 for v in case.values()))
+    x = torch.randn(c["B"], c["T"], c["Cin"], generator=g)
+    w = torch.randn(c["Cout"], c["Cin"], k, generator=g) / math.sqrt(c["Cin"] * k)
+    b = torch.randn(c["Cout"], generator=g)
+    xin = F.leaky_relu(x, 0.1) if c["pre"] == 2 else (F.relu(x) if c["pre"] == 1 else x)
+    xt = xin.transpose(1, 2).double()
+    if c["pad_mode"] != 0:
+        xt = F.pad(xt, (pad, pad), mode={1: "reflect", 2: "replicate"}[c["pad_mode"]])
+        ref = F.conv1d(xt, w.double(), b.double(), dilation=dil)
+    else:
+        ref = F.conv1d(xt, w.double(), b.double(), dilation=dil, padding=pad)
+    ref = ref.transpose(1, 2)
+    if c["post"] == 1:
+        ref = torch.relu(ref)
+    res = torch.randn(ref.shape, generator=g) if c["res"] else None
+    y0 = torch.randn(ref.shape, generator=g) if c["acc"] else None
+    if res is not None:
+        ref = ref + res.double()
+    ref = ref * c["scale"]
+    if y0 is not None:
+        ref = ref + y0.double()
+    kw = dict(k=k, dil=dil, pad=pad, pad_mode=c["pad_mode"], pre_act=c["pre"], pre_slope=0.1, post_act=c["post"],
+              res=res.to(DEV) if res is not None else None, out_scale=c["scale"], accumulate=c["acc"])
+    y_tc = ops.conv1d(x.to(DEV), pack.pack_conv(w).to(DEV), b.to(DEV), out=y0.clone().to(DEV) if y0 is not None else None,
+                      w_tc=pack.pack_conv_tc_planes(w).to(DEV), **kw)
+    y_ff = ops.conv1d(x.to(DEV), pack.pack_conv(w).to(DEV), b.to(DEV), out=y0.clone().to(DEV) if y0 is not None else None, **kw)
+    torch.cuda.synchronize()
+    e_tc = (y_tc.cpu().double() - ref).abs().max().item()
+    e_ff = (y_ff.cpu().double() - ref).abs().max().item()
+    print(f"conv tc err {e_tc:.3e}  ffma err {e_ff:.3e}")
+    assert e_tc < 3e-5 * max(1.0, ref.abs().max().item())
+    assert e_tc < 10 * max(e_ff, 1e-7)
+
+
+def test_conv_stacks_tc_vs_oracle(weights_cpu):
+    """Tensor-core conv engine inside the drivers (shapes large enough to be eligible) vs the CPU oracle."""
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    G = helpers.build_g(weights_cpu("g"), DEV)
+    mel = torch.randn(4, 203, 80, generator=gen(61)) * 2 - 4
+    sd = R.SD(weights_cpu("g"), "vqpe.")
+    _, _, _, codes_ref, ze_ref = R.vqpe_forward(sd, mel, W.G_CFG)
+    for eng in (1, 0):
+        G.vqpe.convnet.engine = eng
+        zq, _, _, codes = G.vqpe(mel.to(DEV))
+        assert torch.equal(codes.cpu(), codes_ref), f"VQ codes differ on engine {eng}"
+    phone = torch.randint(0, 320, (2, 16), generator=gen(62))
+    melp = torch.randn(2, 300, 80, generator=gen(63)) * 2 - 4
+    tc_ref, ctx_ref, _ = R.mrte_tc_latent(R.SD(weights_cpu("g"), "mrte."), phone, melp, W.G_CFG)
+    tc = G.mrte.tc_latent(phone.to(DEV), melp.to(DEV))
+    assert (tc.cpu() - tc_ref).abs().max().item() < 2e-4
+    x = torch.randn(2, 768, 140, generator=gen(64))
+    dec_ref = R.convnet(R.SD(weights_cpu("g"), "decoder."), x, 5, 4, 2)
+    assert (G.decoder(x.to(DEV)).cpu() - dec_ref).abs().max().item() < 5e-4
+
+
+def test_hifigan_tc_vs_oracle(weights_cpu):
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    hifi = helpers.build_hifigan(weights_cpu("hifigan"), DEV)
+    mel = torch.randn(2, 80, 30, generator=gen(65)) * 2 - 4
+    ref = R.hifigan_generator(weights_cpu("hifigan"), mel, W.HIFIGAN_CFG)
+    hifi.generator.engine = 1
+    w1 = hifi.decode_batch(mel.to(DEV))
+    hifi.generator.engine = 0
+    w0 = hifi.decode_batch(mel.to(DEV))
+    assert (w1.cpu() - ref).abs().max().item() < 1e-4
+    assert (w0.cpu() - ref).abs().max().item() < 1e-4

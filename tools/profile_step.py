@@ -24,12 +24,42 @@ def main():
     tts = bench.build_product(dev)
     wav, phone, forced = bench.make_inputs(a.batch, 1234)
     wav, phone, forced = wav.to(dev), phone.to(dev), forced.to(dev)
+    from megatts2_b200 import ops
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
     bench.gpu_step(tts, wav, phone, forced)          # warm-up: plans, workspace, attributes
     torch.cuda.synchronize()
-    torch.cuda.cudart().cudaProfilerStart()
-    bench.gpu_step(tts, wav, phone, forced)
+    rt = torch.cuda.cudart()
+    if a.stage == "all":
+        rt.cudaProfilerStart()
+        bench.gpu_step(tts, wav, phone, forced)
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        return
+    mel = extract_mel_spec(wav, frames_major=True)
+    if a.stage == "mel":
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+        extract_mel_spec(wav, frames_major=True)
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        return
+    tc = tts.generator.mrte.tc_latent(phone, mel)
+    exp = tts.lr(tc, forced)
+    tc8 = ops.maxpool_time(exp, 8)
+    if a.stage == "plm":
+        torch.cuda.synchronize()
+        rt.cudaProfilerStart()
+        tts.plm.infer(tc8)
+        torch.cuda.synchronize()
+        rt.cudaProfilerStop()
+        return
+    codes = tts.plm.infer(tc8)
+    melo = tts.generator.decode_mel_cl(exp, codes)
     torch.cuda.synchronize()
-    torch.cuda.cudart().cudaProfilerStop()
+    rt.cudaProfilerStart()
+    tts.hifi_gan.decode_batch_cl(melo)
+    torch.cuda.synchronize()
+    rt.cudaProfilerStop()
 
 
 if __name__ == "__main__":
