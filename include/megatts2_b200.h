@@ -46,6 +46,10 @@ int mtts_profile_begin(void);
 int mtts_profile_end(double* gemm_ms, double* gemm_flops, int64_t* gemm_launches);
 /* per-engine split of the last profile_end: {ffma_ms, ffma_flops, ffma_launches, tc_ms, tc_flops, tc_launches} */
 int mtts_profile_split(double* out6);
+/* diagnostics: per-launcher CUDA-event trace of everything enqueued between begin and end (single stream);
+ * end synchronises and writes a text table "launcher launches total_ms share" into buf */
+int mtts_trace_begin(void* stream);
+int mtts_trace_end(char* buf, int32_t buf_len);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };
@@ -82,6 +86,8 @@ typedef struct {
    * shape is eligible (stride 1, Cin % 8 == 0, Cin >= 32, Cout in {32, 64, >= 128 and % 32 == 0}). */
   const void* w_tc;
   void* tc_scratch; int64_t tc_scratch_bytes;
+  int64_t tc_rows_cap;                     /* k == 1 only: row capacity of the scratch planes (>= B*Tin, 0 -> B*Tin);
+                                              a stable capacity keeps the cached TMA descriptors valid across AR steps */
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);

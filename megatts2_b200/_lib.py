@@ -29,7 +29,7 @@ class ConvParams(C.Structure):
         ("out_scale", f32), ("accumulate", i32),
         ("out_shift", i64), ("y_batch_elems", i64),
         ("in_lens", vp),
-        ("w_tc", vp), ("tc_scratch", vp), ("tc_scratch_bytes", i64),
+        ("w_tc", vp), ("tc_scratch", vp), ("tc_scratch_bytes", i64), ("tc_rows_cap", i64),
     ]
 
 
@@ -104,6 +104,8 @@ SIGNATURES = {
     "mtts_profile_begin": (C.c_int, []),
     "mtts_profile_end": (C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(i64)]),
     "mtts_profile_split": (C.c_int, [C.POINTER(C.c_double)]),
+    "mtts_trace_begin": (C.c_int, [vp]),
+    "mtts_trace_end": (C.c_int, [C.c_char_p, i32]),
     "mtts_conv1d_f32": (C.c_int, [C.POINTER(ConvParams), vp]),
     "mtts_linear_tc_scratch_bytes": (i64, [i64, i32]),
     "mtts_linear_tc_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, vp, i64, i64, vp]),

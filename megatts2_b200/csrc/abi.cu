@@ -1,11 +1,29 @@
 // C ABI: op-level entry points + library state.  (Composite drivers export theirs from
 // drivers.cu.)  No C++ exception crosses this boundary; errors are negative codes plus a
 // thread-local message.
+#include <algorithm>
+
 #include "kernels.h"
+
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
 
 namespace mtts {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+
+bool g_trace_on = false;
+static std::mutex g_trace_mu;
+static std::vector<std::pair<std::string, cudaEvent_t>> g_trace;
+void trace_record(const char* name, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  cudaEvent_t e;
+  if (cudaEventCreate(&e) != cudaSuccess) return;
+  cudaEventRecord(e, st);
+  g_trace.emplace_back(name, e);
+}
 }  // namespace mtts
 
 using namespace mtts;
@@ -15,6 +33,48 @@ extern "C" {
 int mtts_abi_version(void) { return MTTS_ABI_VERSION; }
 const char* mtts_last_error(void) { return g_err; }
 int64_t mtts_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+/* diagnostics: begin records a start marker on `stream`; end synchronises and writes a table
+ * "launcher  launches  total_ms" (sorted by time) into buf */
+int mtts_trace_begin(void* stream) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  for (auto& t : g_trace) cudaEventDestroy(t.second);
+  g_trace.clear();
+  cudaEvent_t e;
+  cudaEventCreate(&e);
+  cudaEventRecord(e, (cudaStream_t)stream);
+  g_trace.emplace_back("<begin>", e);
+  g_trace_on = true;
+  return 0;
+}
+int mtts_trace_end(char* buf, int32_t buf_len) {
+  std::lock_guard<std::mutex> lk(g_trace_mu);
+  g_trace_on = false;
+  std::map<std::string, std::pair<int, double>> agg;
+  double total = 0.0;
+  for (size_t i = 1; i < g_trace.size(); ++i) {
+    float ms = 0.f;
+    cudaEventSynchronize(g_trace[i].second);
+    cudaEventElapsedTime(&ms, g_trace[i - 1].second, g_trace[i].second);
+    agg[g_trace[i].first].first += 1;
+    agg[g_trace[i].first].second += ms;
+    total += ms;
+  }
+  std::vector<std::pair<double, std::string>> order;
+  for (auto& kv : agg) order.emplace_back(-kv.second.second, kv.first);
+  std::sort(order.begin(), order.end());
+  int off = 0;
+  for (auto& o : order) {
+    auto& v = agg[o.second];
+    off += snprintf(buf + off, off < buf_len ? buf_len - off : 0, "%-28s %7d %10.3f ms %5.1f%%\n", o.second.c_str(), v.first,
+                    v.second, 100.0 * v.second / (total > 0 ? total : 1));
+    if (off >= buf_len) break;
+  }
+  if (off < buf_len) snprintf(buf + off, buf_len - off, "%-28s %7d %10.3f ms\n", "TOTAL", (int)g_trace.size() - 1, total);
+  for (auto& t : g_trace) cudaEventDestroy(t.second);
+  g_trace.clear();
+  return 0;
+}
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream) {
   MTTS_REQUIRE(p, "null params");

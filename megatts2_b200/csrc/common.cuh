@@ -23,9 +23,15 @@ inline int fail(int code, const char* fmt, const char* a = "", long long b = 0, 
     if (!(cond)) return mtts::fail(MTTS_ERR_BAD_ARG, "%s: requirement failed: " msg, __func__); \
   } while (0)
 
+// per-launch event trace (diagnostics; off by default): one event after every launch on its stream,
+// duration(i) = event(i) - event(i-1) since everything runs on one stream
+void trace_record(const char* name, cudaStream_t st);
+extern bool g_trace_on;
+
 #define MTTS_CHECK_LAUNCH()                                                          \
   do {                                                                               \
     mtts::g_launches.fetch_add(1, std::memory_order_relaxed);                        \
+    if (mtts::g_trace_on) mtts::trace_record(__func__, st);                          \
     cudaError_t e__ = cudaGetLastError();                                            \
     if (e__ != cudaSuccess)                                                          \
       return mtts::fail(MTTS_ERR_CUDA, "%s: CUDA launch failed: %lld", __func__, (long long)e__); \

@@ -160,46 +160,51 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
       const int t = tb * 128 + q * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        const int n0 = nb * BN + c * 32;
+        const bool live = (t < g.T) && (n0 < g.Cout);
+        const bool full = live && (n0 + 32 <= g.Cout);
+        float* yr = g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0;
+        const float* rr = g.res ? g.res + (int64_t)b * g.res_sb + (int64_t)t * g.ldr + n0 : nullptr;
+        // All global operands of this chunk are fetched as INDEPENDENT float4 loads before the TMEM read:
+        // a per-element `x += __ldg(bias)` chain costs one exposed L2 round trip per element and was the
+        // bottleneck of the small-channel convs (ncu: long-scoreboard stalls on 64-128 dependent loads per tile).
+        float4 bv[8], rv[8], ov[8];
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            bv[j] = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            rv[j] = rr ? *(reinterpret_cast<const float4*>(rr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            ov[j] = g.accumulate ? *(reinterpret_cast<const float4*>(yr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+        }
         uint32_t r[32], rc[32];
         const uint32_t ta = tmem_base + as * (2 * BN) + c * 32 + ((uint32_t)(q * 32) << 16);
         tmem_ld32(ta, r);
         tmem_ld32(ta + BN, rc);
-        const int n0 = nb * BN + c * 32;
-        if (t < g.T && n0 < g.Cout) {
-          float* yr = g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0;
-          const float* rr = g.res ? g.res + (int64_t)b * g.res_sb + (int64_t)t * g.ldr + n0 : nullptr;
-          if (n0 + 32 <= g.Cout) {
+        if (full) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float v[4];
-#pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                float x = __uint_as_float(r[j + e]) + __uint_as_float(rc[j + e]);
-                if (g.bias) x += __ldg(g.bias + n0 + j + e);
-                v[e] = act_apply(x, g.post_act, 0.f);
-              }
-              if (rr) {
-                const float4 tt = *reinterpret_cast<const float4*>(rr + j);
-                v[0] += tt.x; v[1] += tt.y; v[2] += tt.z; v[3] += tt.w;
-              }
-#pragma unroll
-              for (int e = 0; e < 4; ++e) v[e] *= g.out_scale;
-              if (g.accumulate) {
-                const float4 o = *reinterpret_cast<const float4*>(yr + j);
-                v[0] += o.x; v[1] += o.y; v[2] += o.z; v[3] += o.w;
-              }
-              *reinterpret_cast<float4*>(yr + j) = make_float4(v[0], v[1], v[2], v[3]);
-            }
-          } else {
-            for (int j = 0; j < 32 && n0 + j < g.Cout; ++j) {
-              float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-              if (g.bias) x += __ldg(g.bias + n0 + j);
-              x = act_apply(x, g.post_act, 0.f);
-              if (rr) x += rr[j];
-              x *= g.out_scale;
-              if (g.accumulate) x += yr[j];
-              yr[j] = x;
-            }
+          for (int j = 0; j < 8; ++j) {
+            float v0 = __uint_as_float(r[4 * j + 0]) + __uint_as_float(rc[4 * j + 0]) + bv[j].x;
+            float v1 = __uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1]) + bv[j].y;
+            float v2 = __uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2]) + bv[j].z;
+            float v3 = __uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3]) + bv[j].w;
+            v0 = act_apply(v0, g.post_act, 0.f); v1 = act_apply(v1, g.post_act, 0.f);
+            v2 = act_apply(v2, g.post_act, 0.f); v3 = act_apply(v3, g.post_act, 0.f);
+            v0 = (v0 + rv[j].x) * g.out_scale + ov[j].x;
+            v1 = (v1 + rv[j].y) * g.out_scale + ov[j].y;
+            v2 = (v2 + rv[j].z) * g.out_scale + ov[j].z;
+            v3 = (v3 + rv[j].w) * g.out_scale + ov[j].w;
+            *(reinterpret_cast<float4*>(yr) + j) = make_float4(v0, v1, v2, v3);
+          }
+        } else if (live) {
+          for (int j = 0; j < 32 && n0 + j < g.Cout; ++j) {
+            float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
+            if (g.bias) x += __ldg(g.bias + n0 + j);
+            x = act_apply(x, g.post_act, 0.f);
+            if (rr) x += rr[j];
+            x *= g.out_scale;
+            if (g.accumulate) x += yr[j];
+            yr[j] = x;
           }
         }
       }
@@ -349,8 +354,13 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
   if ((((uintptr_t)p.x) & 15) != 0) return false;
   if (p.Tout != p.Tin + 2 * p.pad - p.dil * (p.k - 1)) return false;
   if ((int64_t)p.B * p.Tout < 128) return false;         // tiny problems stay on the exact FFMA engine
-  const int Tp = p.Tout + p.dil * (p.k - 1);
-  return 3 * (int64_t)p.B * Tp * p.Cin * 2 + 2048 <= p.tc_scratch_bytes;
+  const int64_t Tp = p.Tout + p.dil * (p.k - 1);
+  int64_t rows = (int64_t)p.B * Tp;
+  if (p.tc_rows_cap > 0) {
+    if (p.k != 1 || p.B != 1 || p.tc_rows_cap < rows) return false;
+    rows = p.tc_rows_cap;
+  }
+  return 3 * rows * p.Cin * 2 + 2048 <= p.tc_scratch_bytes;
 }
 
 int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
@@ -358,20 +368,32 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   MTTS_TRY(ctc_init());
   const int halo = p.dil * (p.k - 1);
   const int hl = p.pad, Tp = p.Tout + halo;
+  const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : Tp;     // descriptor rows (>= Tp)
   __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
-  const int64_t plane_stride = (int64_t)p.B * Tp * p.Cin;
+  const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
   {
-    const int64_t total4 = plane_stride / 4;
+    const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
     split_pad_bf16x3_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
                                                                           p.pad_mode, p.pre_act, p.pre_slope, planes,
                                                                           plane_stride, total4);
     MTTS_CHECK_LAUNCH();
   }
-  const int BN = p.Cout >= 128 ? 128 : p.Cout;
   const int SWB = p.Cin >= 64 ? 128 : 64;
+  // N-tile width: the widest tile that still gives every SM a tile; under-filled grids are latency-bound
+  // (one 128x128xK tile per CTA is paced by TMA round trips, not by the tensor pipe), so narrow tiles win there
+  int BN = 32;
+  if (SWB == 128) {
+    const int64_t mt = (int64_t)p.B * cdiv64(p.Tout, 128);
+    const int cands[3] = {128, 64, 32};
+    for (int i = 0; i < 3; ++i) {
+      if (cands[i] > p.Cout) continue;
+      BN = cands[i];
+      if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(g_ctc_sms * 4) / 5) break;
+    }
+  }
   ConvTcMaps maps;
   for (int q = 0; q < 3; ++q) {
-    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp, (uint64_t)p.B, SWB / 2, 128, SWB, &maps.a[q]));
+    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2, 128, SWB, &maps.a[q]));
     MTTS_TRY(cmap_get((const __nv_bfloat16*)p.w_tc + (int64_t)q * p.k * p.Cout * p.Cin, (uint64_t)p.Cin,
                       (uint64_t)p.k * p.Cout, 0, SWB / 2, BN, SWB, &maps.b[q]));
   }
@@ -380,10 +402,26 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.bias = p.bias; a.res = p.res; a.res_sb = p.res_batch_stride; a.ldr = p.ldr;
   a.y = p.y; a.y_sb = p.y_batch_stride; a.ldy = p.ldy;
   a.post_act = p.post_act; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
+  if (SWB == 64) return conv_tc_launch<32, 64>(maps, a, st);
   if (BN == 128) return conv_tc_launch<128, 128>(maps, a, st);
   if (BN == 64) return conv_tc_launch<64, 128>(maps, a, st);
-  if (SWB == 128) return conv_tc_launch<32, 128>(maps, a, st);
-  return conv_tc_launch<32, 64>(maps, a, st);
+  return conv_tc_launch<32, 128>(maps, a, st);
+}
+
+// nn.Linear on the tensor-core engine = the k = 1 case of the tap-GEMM
+int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K) { return 3 * rows_cap * (int64_t)K * 2 + 4096; }
+
+int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,
+              const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,
+              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, cudaStream_t st) {
+  MTTS_REQUIRE(x && w_planes && y && scratch, "null pointer");
+  mtts_conv_params p = linear_params(x, ldx, nullptr, bias, y, ldy, M, K, N);
+  p.w = reinterpret_cast<const float*>(w_planes);     // unused on this path (non-null for validation only)
+  p.res = res; p.ldr = ldr; p.pre_act = pre_act; p.pre_slope = pre_slope; p.post_act = post_act; p.out_scale = out_scale;
+  p.w_tc = w_planes; p.tc_scratch = scratch; p.tc_scratch_bytes = scratch_bytes; p.tc_rows_cap = rows_cap;
+  if (!conv_tc_eligible(p))
+    return fail(MTTS_ERR_UNSUPPORTED, "%s: shape not eligible for the tensor-core engine (M=%lld N=%lld)", "linear_tc", M, N);
+  return conv_tc(p, st);
 }
 
 }  // namespace mtts

@@ -50,30 +50,16 @@ static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
   return linear_tc_scratch_bytes(e->conv_ff ? 5 * rows_cap + 64 : rows_cap, kmax) + 4096;
 }
 
-// dense layer dispatch: tcgen05 bf16x3 when enabled, packed planes exist and the tile is worth it
+// dense layer dispatch: one tap-GEMM call; conv1d() picks the tcgen05 engine when planes + scratch are attached
+// and the shape is eligible (M >= 128), else the exact FFMA engine
 static int lin(const mtts_encoder* e, const TcScratch* tc, const float* x, int ldx, int64_t M, int K, int N,
                const float* w32, const void* wtc, const float* bias, const float* res, int ldr, float* y, int ldy,
                int post_act, cudaStream_t st) {
-  if (e->engine == 1 && tc && tc->p && wtc && M >= 128 && K % 8 == 0 && N % 4 == 0) {
-    ProfRec r;
-    const bool prof = g_prof_on;
-    if (prof) {
-      cudaEventCreate(&r.a); cudaEventCreate(&r.b);
-      r.flops = 2.0 * (double)M * N * K;
-      r.tc = true;
-      cudaEventRecord(r.a, st);
-    }
-    const int rc = linear_tc(x, ldx, M, K, wtc, N, bias, res, ldr, y, ldy, 0, 0.f, post_act, 1.0f, tc->p, tc->bytes,
-                             tc->rows_cap, st);
-    if (prof) {
-      cudaEventRecord(r.b, st);
-      std::lock_guard<std::mutex> lk(g_prof_mu);
-      g_prof.push_back(r);
-    }
-    return rc;
-  }
   mtts_conv_params p = linear_params(x, ldx, w32, bias, y, ldy, M, K, N);
   p.res = res; p.ldr = ldr; p.post_act = post_act;
+  if (e->engine == 1 && tc && tc->p && wtc) {
+    p.w_tc = wtc; p.tc_scratch = tc->p; p.tc_scratch_bytes = tc->bytes; p.tc_rows_cap = tc->rows_cap;
+  }
   return conv1d(p, st);
 }
 
@@ -153,13 +139,20 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       p.y = y; p.ldy = D; p.y_batch_stride = D;
       p.B = B; p.Tin = 1; p.Tout = 1; p.Cin = D; p.Cout = D; p.k = 1; p.stride = 1; p.dil = 1;
       p.out_scale = 1.0f;
+      // M = B rows only: the FFMA engine splits K across CTAs into the tensor-core scratch (when present)
+      auto scratch = [&](mtts_conv_params& q) {
+        if (tc && tc->p) { q.tc_scratch = tc->p; q.tc_scratch_bytes = tc->bytes; }
+      };
+      scratch(p);
       MTTS_TRY(conv1d(p, st));
       MTTS_TRY(layernorm(y, D, L.ln2_g, L.ln2_b, nullptr, 0, h, D, B, D, 1e-5f, 0, 0, st));
       mtts_conv_params p1 = linear_params(h, D, L.w_ff1, L.b_ff1, f, F, B, D, F);
       p1.post_act = MTTS_ACT_RELU;
+      scratch(p1);
       MTTS_TRY(conv1d(p1, st));
       mtts_conv_params p2 = linear_params(f, F, L.w_ff2, L.b_ff2, y, D, B, F, D);
       p2.res = y; p2.ldr = D;
+      scratch(p2);
       MTTS_TRY(conv1d(p2, st));
     }
   }
@@ -206,6 +199,7 @@ static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_l
     p.w = m->w_predict;
     p.y = lg; p.ldy = V; p.y_batch_stride = lg_sb;
     p.B = B; p.Tin = 1; p.Tout = 1; p.Cin = D; p.Cout = V; p.k = 1; p.stride = 1; p.dil = 1; p.out_scale = 1.0f;
+    if (tcs.p) { p.tc_scratch = tcs.p; p.tc_scratch_bytes = tcs.bytes; }
     MTTS_TRY(conv1d(p, st));
     MTTS_TRY(argmax_rows(lg, lg_sb, V, B, codes + (t + 1), T + 1, codes_out + t, T, st));
   }

@@ -62,27 +62,54 @@ __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
 __global__ void __launch_bounds__(MEL_FPB * 32)
 mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L, int F, const float* __restrict__ window,
            const float* __restrict__ fb_w, const int32_t* __restrict__ fb_off, const int32_t* __restrict__ fb_start,
-           int n_mels, float clamp_min, float* __restrict__ out, int64_t out_sb, int64_t out_sm, int64_t out_sf) {
+           int n_mels, float clamp_min, float* __restrict__ out, int64_t out_sb, int64_t out_sm, int64_t out_sf,
+           int vec_ok) {
   constexpr int SPAN = MEL_NFFT + (MEL_FPB - 1) * MEL_HOP;   // 2816
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                                  // [SPAN]
   float* win = xs + SPAN;                            // [1024]
   float2* zb = reinterpret_cast<float2*>(win + MEL_NFFT);   // [FPB][ZPAD]
   float* mag = reinterpret_cast<float*>(zb + MEL_FPB * MEL_ZPAD);   // [FPB][MAGP]
-  float* otile = mag + MEL_FPB * MEL_MAGP;           // [n_mels][FPB]
+  float* otile = mag + MEL_FPB * MEL_MAGP;           // [128][FPB]
+  float* fbw_s = otile + 128 * MEL_FPB;              // [<= 1536] banded filterbank taps
 
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * MEL_FPB;
   const float* wv = wav + (int64_t)b * wav_sb;
   const int g0 = f0 * MEL_HOP - MEL_NFFT / 2;
-  for (int i = tid; i < SPAN; i += MEL_FPB * 32) {
-    int g = g0 + i;
-    if (g < 0) g = -g;
-    if (g >= L) g = 2 * (L - 1) - g;
-    xs[i] = (g >= 0 && g < L) ? __ldg(wv + g) : 0.f;
+  // stage the CTA's sample span.  Interior tiles (no reflection, 16-byte aligned) use batched float4 loads so
+  // that all of a thread's global requests are in flight together; edge tiles take the scalar reflect path.
+  const bool interior = vec_ok && g0 >= 0 && (g0 + SPAN) <= L;
+  if (interior) {
+    constexpr int NV = SPAN / 4;                               // 704 float4
+    constexpr int PER = (NV + MEL_FPB * 32 - 1) / (MEL_FPB * 32);
+    const float4* src = reinterpret_cast<const float4*>(wv + g0);
+    float4 v[PER];
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * MEL_FPB * 32;
+      if (i < NV) v[q] = __ldg(src + i);
+    }
+#pragma unroll
+    for (int q = 0; q < PER; ++q) {
+      const int i = tid + q * MEL_FPB * 32;
+      if (i < NV) *reinterpret_cast<float4*>(xs + 4 * i) = v[q];
+    }
+  } else {
+    for (int i = tid; i < SPAN; i += MEL_FPB * 32) {
+      int g = g0 + i;
+      if (g < 0) g = -g;
+      if (g >= L) g = 2 * (L - 1) - g;
+      xs[i] = (g >= 0 && g < L) ? __ldg(wv + g) : 0.f;
+    }
   }
-  for (int i = tid; i < MEL_NFFT; i += MEL_FPB * 32) win[i] = __ldg(window + i);
+  {
+    const float4* wsrc = reinterpret_cast<const float4*>(window);   // 1024 floats, 16-byte aligned (checked on host)
+    *reinterpret_cast<float4*>(win + 4 * tid) = __ldg(wsrc + tid);  // 256 threads x float4 = 1024
+  }
+  const int n_taps = min(fb_off[n_mels], 1536);      // taps beyond the staged window fall back to global loads
+  for (int i = tid; i < n_taps; i += MEL_FPB * 32) fbw_s[i] = __ldg(fb_w + i);
   __syncthreads();
 
   const int f = f0 + w;
@@ -162,7 +189,7 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L, int F, const fl
     for (int m = lane; m < n_mels; m += 32) {
       const int o0 = fb_off[m], o1 = fb_off[m + 1], s0 = fb_start[m];
       float acc = 0.f;
-      for (int i = o0; i < o1; ++i) acc = fmaf(mg[s0 + (i - o0)], __ldg(fb_w + i), acc);
+      for (int i = o0; i < o1; ++i) acc = fmaf(mg[s0 + (i - o0)], i < 1536 ? fbw_s[i] : __ldg(fb_w + i), acc);
       otile[m * MEL_FPB + w] = logf(fmaxf(acc, clamp_min));
     }
   }
@@ -192,10 +219,12 @@ int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float*
   MTTS_REQUIRE(L > MEL_NFFT / 2, "reflect padding needs L > n_fft/2 (torch.stft center=True)");
   MTTS_REQUIRE(n_mels > 0 && n_mels <= 128, "n_mels out of range");
   MTTS_REQUIRE(B >= 0 && B <= 65535 * 32, "bad batch");
+  MTTS_REQUIRE((((uintptr_t)window) & 15) == 0, "window table must be 16-byte aligned");
+  const int vec_ok = ((((uintptr_t)wav) & 15) == 0) && (wav_sb % 4 == 0);
   if (B == 0) return 0;
   const int F = 1 + L / MEL_HOP;
   const size_t smem = sizeof(float) * ((MEL_NFFT + (MEL_FPB - 1) * MEL_HOP) + MEL_NFFT + 2 * MEL_FPB * MEL_ZPAD +
-                                       MEL_FPB * MEL_MAGP + 128 * MEL_FPB);
+                                       MEL_FPB * MEL_MAGP + 128 * MEL_FPB + 1536);
   {
     std::lock_guard<std::mutex> lk(g_mel_mu);
     int dev = 0;
@@ -215,7 +244,7 @@ int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float*
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     dim3 grid((unsigned)cdiv64(F, MEL_FPB), (unsigned)nb);
     mel_kernel<<<grid, MEL_FPB * 32, smem, st>>>(wav + (int64_t)b0 * wav_sb, wav_sb, L, F, window, fb_w, fb_off, fb_start,
-                                               n_mels, clamp_min, out + (int64_t)b0 * out_sb, out_sb, out_sm, out_sf);
+                                               n_mels, clamp_min, out + (int64_t)b0 * out_sb, out_sb, out_sm, out_sf, vec_ok);
     MTTS_CHECK_LAUNCH();
   }
   return 0;

@@ -92,28 +92,38 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
 }
 
 // ------------------------------------------------------------------------------------------
-// Attention, fp32, online softmax.  CTA = 4 warps = 16 query rows of one (b, h); K/V stream
-// through shared memory 32 keys at a time; lane l scores key l, then owns output dims
-// l + 32*i.  Head dims on the path: 64 (PLM), 96 (ADM), 256 (phone encoder), 512 (MRTE
-// cross-attention, Tk ~ 32: whole K/V in one or two tiles).
-template <int NI>
-__global__ void __launch_bounds__(128) attn_kernel(const mtts_attn_params p) {
+// Attention, fp32, online softmax.  CTA = NW warps x RW query rows of one (b, h); K/V stream through
+// shared memory 32 keys at a time (float4 global loads when aligned); lane l scores key l, then owns
+// output dims l + 32*i.  Head dims on the path: 64 (PLM), 96 (ADM), 256 (phone encoder), 512 (MRTE
+// cross-attention, Tk ~ 32).  For dh <= 128 a CTA covers 64 query rows, i.e. a whole AR-step sequence:
+// K and V are read once per (b, h).
+template <int NI, int RW, int NW>
+__global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p, const int vec) {
   constexpr int DH = 32 * NI;
-  constexpr int BQ = 16, BKV = 32, RW = 4;
+  constexpr int BQ = RW * NW, BKV = 32, NT = NW * 32;
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                        // [BQ][DH]
   float* Ks = Qs + BQ * DH;              // [BKV][DH+1]
   float* Vs = Ks + BKV * (DH + 1);       // [BKV][DH]
-  float* Ps = Vs + BKV * DH;             // [4][RW][32]
+  float* Ps = Vs + BKV * DH;             // [NW][RW][32]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const float* qb = p.q + (int64_t)b * p.q_sb + (int64_t)h * DH;
   const float* kb = p.k + (int64_t)b * p.k_sb + (int64_t)h * DH;
   const float* vb = p.v + (int64_t)b * p.v_sb + (int64_t)h * DH;
 
-  for (int i = tid; i < BQ * DH; i += 128) {
-    const int r = i / DH, d = i - r * DH;
-    Qs[i] = (q0 + r < p.Tq) ? qb[(int64_t)(q0 + r) * p.q_st + d] : 0.f;
+  if (vec) {
+    for (int i = tid; i < BQ * (DH / 4); i += NT) {
+      const int r = i / (DH / 4), d = (i - r * (DH / 4)) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (q0 + r < p.Tq) v = *reinterpret_cast<const float4*>(qb + (int64_t)(q0 + r) * p.q_st + d);
+      *reinterpret_cast<float4*>(Qs + r * DH + d) = v;
+    }
+  } else {
+    for (int i = tid; i < BQ * DH; i += NT) {
+      const int r = i / DH, d = i - r * DH;
+      Qs[i] = (q0 + r < p.Tq) ? qb[(int64_t)(q0 + r) * p.q_st + d] : 0.f;
+    }
   }
   float m_run[RW], l_run[RW], acc[RW][NI];
 #pragma unroll
@@ -129,16 +139,32 @@ __global__ void __launch_bounds__(128) attn_kernel(const mtts_attn_params p) {
     const int qr = min(q0 + w * RW + i, p.Tq - 1);
     mrow[i] = p.mask ? p.mask + (int64_t)b * p.mask_sb + (int64_t)h * p.mask_sh + (int64_t)qr * p.mask_sq : nullptr;
   }
+  const bool warp_live = (q0 + w * RW) < p.Tq;   // warp-uniform: this warp owns at least one real query row
 
   for (int k0 = 0; k0 < p.Tk; k0 += BKV) {
     __syncthreads();   // previous tile fully consumed (also orders the Q fill)
-    for (int i = tid; i < BKV * DH; i += 128) {
-      const int r = i / DH, d = i - r * DH;
-      const bool ok = k0 + r < p.Tk;
-      Ks[r * (DH + 1) + d] = ok ? kb[(int64_t)(k0 + r) * p.k_st + d] : 0.f;
-      Vs[r * DH + d] = ok ? vb[(int64_t)(k0 + r) * p.v_st + d] : 0.f;
+    if (vec) {
+      for (int i = tid; i < BKV * (DH / 4); i += NT) {
+        const int r = i / (DH / 4), d = (i - r * (DH / 4)) * 4;
+        float4 kv = make_float4(0.f, 0.f, 0.f, 0.f), vv = kv;
+        if (k0 + r < p.Tk) {
+          kv = *reinterpret_cast<const float4*>(kb + (int64_t)(k0 + r) * p.k_st + d);
+          vv = *reinterpret_cast<const float4*>(vb + (int64_t)(k0 + r) * p.v_st + d);
+        }
+        float* kd = Ks + r * (DH + 1) + d;
+        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+        *reinterpret_cast<float4*>(Vs + r * DH + d) = vv;
+      }
+    } else {
+      for (int i = tid; i < BKV * DH; i += NT) {
+        const int r = i / DH, d = i - r * DH;
+        const bool ok = k0 + r < p.Tk;
+        Ks[r * (DH + 1) + d] = ok ? kb[(int64_t)(k0 + r) * p.k_st + d] : 0.f;
+        Vs[r * DH + d] = ok ? vb[(int64_t)(k0 + r) * p.v_st + d] : 0.f;
+      }
     }
     __syncthreads();
+    if (!warp_live) continue;
     float s[RW];
 #pragma unroll
     for (int i = 0; i < RW; ++i) s[i] = 0.f;
@@ -193,18 +219,22 @@ __global__ void __launch_bounds__(128) attn_kernel(const mtts_attn_params p) {
   }
 }
 
-template <int NI>
+template <int NI, int RW, int NW>
 static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   constexpr int DH = 32 * NI;
-  const size_t smem = sizeof(float) * (16 * DH + 32 * (DH + 1) + 32 * DH + 4 * 4 * 32);
+  constexpr int BQ = RW * NW;
+  const size_t smem = sizeof(float) * (BQ * DH + 32 * (DH + 1) + 32 * DH + NW * RW * 32);
   static bool configured = false;   // per-process, per-instantiation; attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI, RW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "attention", (long long)e);
     configured = true;
   }
-  dim3 grid((unsigned)cdiv64(p.Tq, 16), (unsigned)p.H, (unsigned)p.B);
-  attn_kernel<NI><<<grid, 128, smem, st>>>(p);
+  auto al = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
+  const int vec = al(p.q) && al(p.k) && al(p.v) && p.q_st % 4 == 0 && p.k_st % 4 == 0 && p.v_st % 4 == 0 &&
+                  p.q_sb % 4 == 0 && p.k_sb % 4 == 0 && p.v_sb % 4 == 0;
+  dim3 grid((unsigned)cdiv64(p.Tq, BQ), (unsigned)p.H, (unsigned)p.B);
+  attn_kernel<NI, RW, NW><<<grid, NW * 32, smem, st>>>(p, vec);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -215,11 +245,13 @@ int attention(const mtts_attn_params& p, cudaStream_t st) {
   MTTS_REQUIRE(p.H <= 65535 && p.B <= 65535, "grid too large");
   if (p.B == 0 || p.Tq == 0) return 0;
   switch (p.dh) {
-    case 64: return attn_launch<2>(p, st);
-    case 96: return attn_launch<3>(p, st);
-    case 128: return attn_launch<4>(p, st);
-    case 256: return attn_launch<8>(p, st);
-    case 512: return attn_launch<16>(p, st);
+    // dh <= 128: 64 query rows per CTA when the sequence is longer than 16 rows; single-row (AR last position)
+    // and short sequences keep the 16-row CTA
+    case 64: return p.Tq > 16 ? attn_launch<2, 8, 8>(p, st) : attn_launch<2, 4, 4>(p, st);
+    case 96: return p.Tq > 16 ? attn_launch<3, 8, 8>(p, st) : attn_launch<3, 4, 4>(p, st);
+    case 128: return p.Tq > 16 ? attn_launch<4, 8, 8>(p, st) : attn_launch<4, 4, 4>(p, st);
+    case 256: return attn_launch<8, 4, 4>(p, st);
+    case 512: return attn_launch<16, 4, 4>(p, st);
     default: return fail(MTTS_ERR_UNSUPPORTED, "%s: head dim %lld not in {64,96,128,256,512}", "attention", p.dh);
   }
 }

@@ -17,6 +17,8 @@ namespace mtts {
 
 struct ConvFlags {
   int vec_a, vec_b, vec_y;
+  int kk_per_split;        // split-K: reduction slices per blockIdx.z (0 = no split)
+  float* partial;          // split-K: raw partial sums [splits][M][Cout]
 };
 
 __device__ __forceinline__ int map_row(int ti, int len, int mode) {
@@ -46,7 +48,9 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
   const int64_t m0 = (int64_t)blockIdx.x * BM;
   const int n0 = blockIdx.y * BN;
   const int nchunk = (p.Cin + BK - 1) / BK;
-  const int nk = p.k * nchunk;
+  const int nk_all = p.k * nchunk;
+  const int kk_lo = fl.kk_per_split ? blockIdx.z * fl.kk_per_split : 0;
+  const int nk = fl.kk_per_split ? min(nk_all, kk_lo + fl.kk_per_split) : nk_all;
 
   // ---- per-thread A rows (fixed for the whole K loop)
   int64_t a_base[A_IT];
@@ -147,11 +151,11 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
 
-  load_regs(0);
+  load_regs(kk_lo);
   store_smem(0);
   __syncthreads();
   int cur = 0;
-  for (int kk = 0; kk < nk; ++kk) {
+  for (int kk = kk_lo; kk < nk; ++kk) {
     if (kk + 1 < nk) load_regs(kk + 1);
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
@@ -176,6 +180,24 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
     cur ^= 1;
   }
 
+  // ---- split-K: raw partial sums only (the epilogue runs in splitk_reduce_kernel)
+  if (fl.partial) {
+    float* part = fl.partial + (int64_t)blockIdx.z * M * p.Cout;
+#pragma unroll
+    for (int i = 0; i < TM; ++i) {
+      const int row = (i / 4) * (BM / MG) + ty * 4 + (i & 3);
+      const int64_t m = m0 + row;
+      if (m >= M) continue;
+#pragma unroll
+      for (int g = 0; g < NG; ++g) {
+        const int n = n0 + g * (BN / NG) + tx * 4;
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < p.Cout) part[m * p.Cout + n + e] = acc[i][g * 4 + e];
+      }
+    }
+    return;
+  }
   // ---- epilogue
   const int64_t ybe = p.y_batch_elems ? p.y_batch_elems : (int64_t)p.Tout * p.ldy;
 #pragma unroll
@@ -228,6 +250,28 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
   }
 }
 
+
+
+// split-K second pass: fixed-order sum of the partials (deterministic), then the usual epilogue
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const mtts_conv_params p, const float* __restrict__ partial, int splits) {
+  const int64_t M = (int64_t)p.B * p.Tout;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= M * p.Cout) return;
+  const int64_t m = i / p.Cout;
+  const int n = (int)(i - m * p.Cout);
+  float v = 0.f;
+  for (int z = 0; z < splits; ++z) v += partial[((int64_t)z * M + m) * p.Cout + n];
+  const int b = (int)(m / p.Tout), t = (int)(m - (int64_t)b * p.Tout);
+  if (p.bias) v += __ldg(p.bias + n);
+  v = act_apply(v, p.post_act, p.post_slope);
+  if (p.res) v += p.res[(int64_t)b * p.res_batch_stride + (int64_t)t * p.ldr + n];
+  v *= p.out_scale;
+  float* dst = p.y + (int64_t)b * p.y_batch_stride + (int64_t)t * p.ldy + n;
+  if (p.accumulate) v += *dst;
+  *dst = v;
+}
+
 template <int BM, int BN, int TM, int TN>
 static int launch_cfg(const mtts_conv_params& p, const ConvFlags& fl, cudaStream_t st) {
   const int64_t M = (int64_t)p.B * p.Tout;
@@ -249,11 +293,37 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st) {
   if (M == 0) return 0;
   MTTS_REQUIRE(M < (int64_t)2147483647 * 32, "too many rows");
   ConvFlags fl;
+  fl.kk_per_split = 0;
+  fl.partial = nullptr;
   fl.vec_a = (p.Cin % 4 == 0) && (p.ldx % 4 == 0) && (p.x_batch_stride % 4 == 0) && al16(p.x);
   fl.vec_b = (p.Cout % 4 == 0) && al16(p.w);
   fl.vec_y = (p.Cout % 4 == 0) && (p.ldy % 4 == 0) && (p.y_batch_stride % 4 == 0) && al16(p.y) &&
              (p.out_shift % 4 == 0) && (p.y_batch_elems % 4 == 0) &&
              (!p.res || ((p.ldr % 4 == 0) && (p.res_batch_stride % 4 == 0) && al16(p.res)));
+  // Small-M linear layers (the last-position GEMMs of the AR loops: M = batch rows): a 64x64 tile grid leaves
+  // most SMs idle and every CTA walks all of K serially.  Split K over blockIdx.z into the caller's scratch and
+  // reduce in a fixed order (bit-reproducible), so ~all SMs stream a slice of the weights.
+  {
+    const int64_t tiles64 = cdiv64(M, 64) * cdiv64(p.Cout, 64);
+    const int nk = (p.Cin + 15) / 16;
+    if (p.k == 1 && p.stride == 1 && p.pad == 0 && p.out_shift == 0 && !p.in_lens && M <= 256 && tiles64 <= 74 &&
+        nk >= 16 && p.tc_scratch) {
+      int splits = (int)(148 / tiles64);
+      if (splits > 16) splits = 16;
+      if (splits > nk / 4) splits = nk / 4;
+      if (splits >= 2 && (int64_t)splits * M * p.Cout * 4 + 256 <= p.tc_scratch_bytes) {
+        fl.kk_per_split = (nk + splits - 1) / splits;
+        splits = (nk + fl.kk_per_split - 1) / fl.kk_per_split;
+        fl.partial = reinterpret_cast<float*>((((uintptr_t)p.tc_scratch) + 255) & ~(uintptr_t)255);
+        dim3 grid((unsigned)cdiv64(M, 64), (unsigned)cdiv64(p.Cout, 64), (unsigned)splits);
+        tapconv_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(p, fl);
+        MTTS_CHECK_LAUNCH();
+        splitk_reduce_kernel<<<(unsigned)cdiv64(M * p.Cout, 256), 256, 0, st>>>(p, fl.partial, splits);
+        MTTS_CHECK_LAUNCH();
+        return 0;
+      }
+    }
+  }
   const int64_t tiles128 = cdiv64(M, 128) * cdiv64(p.Cout, 128);
   if (p.Cout <= 32) return launch_cfg<128, 32, 8, 4>(p, fl, st);
   if (p.Cout <= 64) return launch_cfg<128, 64, 8, 4>(p, fl, st);

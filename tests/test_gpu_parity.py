@@ -61,7 +61,10 @@ CONV_CASES = [
     dict(B=2, T=200, Cin=64, Cout=64, k=11, dil=5, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),
     dict(B=2, T=333, Cin=32, Cout=32, k=3, dil=3, pad_mode=1, pre=2),            # 128x32 tiles
     dict(B=1, T=97, Cin=7, Cout=5, k=3),                                         # scalar loads both sides
-    dict(B=5, T=1, Cin=768, Cout=768, k=1, res=True),                            # last-row GEMM shape
+    dict(B=5, T=1, Cin=768, Cout=768, k=1, res=True),                            # last-row GEMM shape (skinny kernel)
+    dict(B=64, T=1, Cin=4096, Cout=1024, k=1, res=True),                         # PLM final-layer FF2, skinny kernel
+    dict(B=1, T=64, Cin=1024, Cout=4096, k=1, post=1),                           # PLM final-layer FF1, skinny kernel
+    dict(B=16, T=2, Cin=1000, Cout=1000, k=1),                                   # skinny kernel, K and N tails
     dict(B=2, T=64, Cin=80, Cout=512, k=7, pad_mode=1),                          # conv_pre
     dict(B=2, T=50, Cin=16, Cout=24, k=5, pad_mode=2),                           # replicate padding
 ]
@@ -92,6 +95,8 @@ def test_conv1d_vs_torch(case):
     ref = ref.transpose(1, 2)
     if c["post"] == 3:
         ref = torch.tanh(ref)
+    elif c["post"] == 1:
+        ref = torch.relu(ref)
     res = torch.randn(ref.shape, generator=g) if c["res"] else None
     y0 = torch.randn(ref.shape, generator=g) if c["acc"] else None
     if res is not None:

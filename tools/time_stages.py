@@ -54,6 +54,15 @@ def main():
         say(f"  launches this pass: {ops.launch_count() - n0}; wav {tuple(wv.shape)} finite={bool(torch.isfinite(wv).all())}")
     _, dt = timed("full gpu_step", lambda: bench.gpu_step(tts, wav, phone, forced))
     say(f"samples/s = {a.batch * bench.SAMPLES_PER_UTT / dt:.0f}")
+    import ctypes as C
+    from megatts2_b200 import _lib as L
+    lib = L.lib()
+    lib.mtts_trace_begin(ops._stream())
+    bench.gpu_step(tts, wav, phone, forced)
+    buf = C.create_string_buffer(16384)
+    lib.mtts_trace_end(buf, 16384)
+    say("== per-launcher event trace of one step (event overhead included)")
+    say(buf.value.decode())
 
 
 if __name__ == "__main__":
