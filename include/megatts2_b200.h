@@ -88,6 +88,13 @@ typedef struct {
   void* tc_scratch; int64_t tc_scratch_bytes;
   int64_t tc_rows_cap;                     /* k == 1 only: row capacity of the scratch planes (>= B*Tin, 0 -> B*Tin);
                                               a stable capacity keeps the cached TMA descriptors valid across AR steps */
+  /* plane fusion (tensor-core engine only).  tc_presplit = 1: the activation planes already sit in tc_scratch
+   * (three planes of (B, Tout + dil*(k-1), Cin) bf16, padding materialised, pre-activation applied) - x is not
+   * read.  tc_out_planes != NULL: the epilogue additionally writes act(result) as three bf16 planes for the next
+   * tensor-core layer (row (b*tc_out_tp + tc_out_hl + t), stride tc_out_ld); y may then be NULL. */
+  int32_t tc_presplit;
+  void* tc_out_planes; int64_t tc_out_plane_stride;
+  int32_t tc_out_ld, tc_out_tp, tc_out_hl, tc_out_act; float tc_out_slope;
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);
@@ -122,6 +129,9 @@ typedef struct {
   const float* mask; int64_t mask_sb, mask_sh, mask_sq;
   int32_t B, H, Tq, Tk, dh;
   float scale;
+  /* optional: write the output as three bf16 planes (row b*Tq + t, stride o_planes_ld) for a following
+   * tensor-core GEMM; o may then be NULL */
+  void* o_planes; int64_t o_plane_stride; int32_t o_planes_ld;
 } mtts_attn_params;
 int mtts_attention_f32(const mtts_attn_params* p, void* stream);
 

@@ -30,6 +30,8 @@ class ConvParams(C.Structure):
         ("out_shift", i64), ("y_batch_elems", i64),
         ("in_lens", vp),
         ("w_tc", vp), ("tc_scratch", vp), ("tc_scratch_bytes", i64), ("tc_rows_cap", i64),
+        ("tc_presplit", i32), ("tc_out_planes", vp), ("tc_out_plane_stride", i64),
+        ("tc_out_ld", i32), ("tc_out_tp", i32), ("tc_out_hl", i32), ("tc_out_act", i32), ("tc_out_slope", f32),
     ]
 
 
@@ -42,6 +44,7 @@ class AttnParams(C.Structure):
         ("mask", vp), ("mask_sb", i64), ("mask_sh", i64), ("mask_sq", i64),
         ("B", i32), ("H", i32), ("Tq", i32), ("Tk", i32), ("dh", i32),
         ("scale", f32),
+        ("o_planes", vp), ("o_plane_stride", i64), ("o_planes_ld", i32),
     ]
 
 

@@ -27,6 +27,8 @@ struct ConvTcArgs {
   const float* res; int64_t res_sb; int32_t ldr;
   float* y; int64_t y_sb; int32_t ldy;
   int32_t post_act; float out_scale; int32_t accumulate;
+  // optional bf16x3 copy of the result for the next tensor-core layer
+  __nv_bfloat16* op; int64_t op_stride; int32_t op_ld, op_tp, op_hl, op_act; float op_slope;
 };
 
 template <int BN, int SWB>
@@ -163,7 +165,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
         const int n0 = nb * BN + c * 32;
         const bool live = (t < g.T) && (n0 < g.Cout);
         const bool full = live && (n0 + 32 <= g.Cout);
-        float* yr = g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0;
+        float* yr = g.y ? g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0 : nullptr;
         const float* rr = g.res ? g.res + (int64_t)b * g.res_sb + (int64_t)t * g.ldr + n0 : nullptr;
         // All global operands of this chunk are fetched as INDEPENDENT float4 loads before the TMEM read:
         // a per-element `x += __ldg(bias)` chain costs one exposed L2 round trip per element and was the
@@ -194,7 +196,12 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
             v1 = (v1 + rv[j].y) * g.out_scale + ov[j].y;
             v2 = (v2 + rv[j].z) * g.out_scale + ov[j].z;
             v3 = (v3 + rv[j].w) * g.out_scale + ov[j].w;
-            *(reinterpret_cast<float4*>(yr) + j) = make_float4(v0, v1, v2, v3);
+            if (yr) *(reinterpret_cast<float4*>(yr) + j) = make_float4(v0, v1, v2, v3);
+            if (g.op) {
+              const float pv[4] = {act_apply(v0, g.op_act, g.op_slope), act_apply(v1, g.op_act, g.op_slope),
+                                   act_apply(v2, g.op_act, g.op_slope), act_apply(v3, g.op_act, g.op_slope)};
+              store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + t) * g.op_ld + n0 + 4 * j, pv);
+            }
           }
         } else if (live) {
           for (int j = 0; j < 32 && n0 + j < g.Cout; ++j) {
@@ -204,7 +211,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
             if (rr) x += rr[j];
             x *= g.out_scale;
             if (g.accumulate) x += yr[j];
-            yr[j] = x;
+            if (yr) yr[j] = x;
           }
         }
       }
@@ -346,12 +353,14 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
 bool conv_tc_eligible(const mtts_conv_params& p) {
   if (!p.w_tc || !p.tc_scratch) return false;
   if (p.stride != 1 || p.out_shift != 0 || p.in_lens) return false;
-  if (p.Cin % 8 != 0 || p.Cin < 32 || p.ldx % 4 != 0 || (p.x_batch_stride % 4) != 0) return false;
+  if (p.Cin % 8 != 0 || p.Cin < 32) return false;
+  if (!p.tc_presplit && (p.ldx % 4 != 0 || (p.x_batch_stride % 4) != 0 || (((uintptr_t)p.x) & 15) != 0)) return false;
   if (!(p.Cout == 32 || p.Cout == 64 || (p.Cout >= 128 && p.Cout % 32 == 0))) return false;
   if (p.Cin < 64 && p.Cout != 32) return false;          // the SWB=64 variant is instantiated for BN=32 only
-  if (p.ldy % 4 != 0 || p.y_batch_stride % 4 != 0 || (((uintptr_t)p.y) & 15) != 0) return false;
+  if (p.y && (p.ldy % 4 != 0 || p.y_batch_stride % 4 != 0 || (((uintptr_t)p.y) & 15) != 0)) return false;
+  if (!p.y && (!p.tc_out_planes || p.accumulate)) return false;
+  if (p.tc_out_planes && (p.Cout % 32 != 0 || p.tc_out_ld % 4 != 0 || p.tc_out_plane_stride % 4 != 0)) return false;
   if (p.res && (p.ldr % 4 != 0 || p.res_batch_stride % 4 != 0 || (((uintptr_t)p.res) & 15) != 0)) return false;
-  if ((((uintptr_t)p.x) & 15) != 0) return false;
   if (p.Tout != p.Tin + 2 * p.pad - p.dil * (p.k - 1)) return false;
   if ((int64_t)p.B * p.Tout < 128) return false;         // tiny problems stay on the exact FFMA engine
   const int64_t Tp = p.Tout + p.dil * (p.k - 1);
@@ -371,7 +380,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : Tp;     // descriptor rows (>= Tp)
   __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
   const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
-  {
+  if (!p.tc_presplit) {
     const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
     split_pad_bf16x3_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
                                                                           p.pad_mode, p.pre_act, p.pre_slope, planes,
@@ -402,6 +411,8 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.bias = p.bias; a.res = p.res; a.res_sb = p.res_batch_stride; a.ldr = p.ldr;
   a.y = p.y; a.y_sb = p.y_batch_stride; a.ldy = p.ldy;
   a.post_act = p.post_act; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
+  a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
+  a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   if (SWB == 64) return conv_tc_launch<32, 64>(maps, a, st);
   if (BN == 128) return conv_tc_launch<128, 128>(maps, a, st);
   if (BN == 64) return conv_tc_launch<64, 128>(maps, a, st);

@@ -47,7 +47,39 @@ static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
   if (e->engine != 1) return 0;
   const int kmax = e->ff_dim > e->d_model ? e->ff_dim : e->d_model;
   // conv-FF (k = 5): padded planes need 4 halo rows per sequence; rows_cap + 4*rows_cap covers any batch split
-  return linear_tc_scratch_bytes(e->conv_ff ? 5 * rows_cap + 64 : rows_cap, kmax) + 4096;
+  if (e->conv_ff) return linear_tc_scratch_bytes(5 * rows_cap + 64, kmax) + 4096;
+  // linear FF, fused plane flow: P_a (rows_cap x D) and P_b (rows_cap x F), three bf16 planes each
+  return 6 * rows_cap * ((int64_t)e->d_model + e->ff_dim) + 8192;
+}
+
+// tensor-core GEMM on planes that a producer kernel already wrote (no split pass); optional plane output
+static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int K, int N, const void* wtc,
+                      const float* bias, const float* res, int ldr, float* y, int ldy, int post_act,
+                      __nv_bfloat16* out_planes, int out_ld, cudaStream_t st) {
+  mtts_conv_params p = linear_params(nullptr, K, nullptr, bias, y, ldy, M, K, N);
+  p.res = res; p.ldr = ldr; p.post_act = post_act;
+  p.w_tc = wtc; p.tc_scratch = planes; p.tc_scratch_bytes = 6 * tc->rows_cap * (int64_t)K + 4096; p.tc_rows_cap = tc->rows_cap;
+  p.tc_presplit = 1;
+  if (out_planes) {
+    p.tc_out_planes = out_planes; p.tc_out_plane_stride = tc->rows_cap * (int64_t)out_ld; p.tc_out_ld = out_ld;
+    p.tc_out_tp = (int32_t)tc->rows_cap; p.tc_out_hl = 0; p.tc_out_act = MTTS_ACT_NONE;
+  }
+  if (!conv_tc_eligible(p))
+    return fail(MTTS_ERR_UNSUPPORTED, "%s: fused tensor-core layer not eligible (M=%lld N=%lld)", "encoder", M, N);
+  ProfRec r;
+  const bool prof = g_prof_on;
+  if (prof) {
+    cudaEventCreate(&r.a); cudaEventCreate(&r.b);
+    r.flops = 2.0 * (double)M * N * K; r.tc = true;
+    cudaEventRecord(r.a, st);
+  }
+  const int rc = conv_tc(p, st);
+  if (prof) {
+    cudaEventRecord(r.b, st);
+    std::lock_guard<std::mutex> lk(g_prof_mu);
+    g_prof.push_back(r);
+  }
+  return rc;
 }
 
 // dense layer dispatch: one tap-GEMM call; conv1d() picks the tcgen05 engine when planes + scratch are attached
@@ -88,12 +120,30 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "encoder", ar.off);
   const float scale = 1.0f / sqrtf((float)dh);
   const float* xin = x;
+  // Fused plane flow (tensor-core engine, linear FF, M >= 128): LayerNorm / attention / the FF1 epilogue write
+  // their result directly as bf16x3 planes, so no split pass and no fp32 round trip feeds the GEMMs.
+  bool fused = e->engine == 1 && !e->conv_ff && tc && tc->p && M >= 128 && D % 32 == 0 && F % 32 == 0 &&
+               tc->bytes >= 6 * tc->rows_cap * ((int64_t)D + F) + 8192 && tc->rows_cap >= M;
+  for (int l = 0; fused && l < e->n_layers; ++l)
+    fused = e->layers[l].w_qkv_tc && e->layers[l].w_o_tc && e->layers[l].w_ff1_tc && e->layers[l].w_ff2_tc;
+  __nv_bfloat16* Pa = nullptr;
+  __nv_bfloat16* Pb = nullptr;
+  if (fused) {
+    Pa = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)tc->p) + 1023) & ~(uintptr_t)1023);
+    Pb = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)(Pa + 3 * tc->rows_cap * (int64_t)D)) + 1023) & ~(uintptr_t)1023);
+  }
+  const PlanesOut pa_out{Pa, tc ? tc->rows_cap * (int64_t)D : 0, D, MTTS_ACT_NONE, 0.f};
   for (int l = 0; l < e->n_layers; ++l) {
     const mtts_encoder_layer& L = e->layers[l];
     const bool last = last_row_only && (l == e->n_layers - 1);
-    // h = LN1(x);  qkv = h Wqkv + b
-    MTTS_TRY(layernorm(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
-    MTTS_TRY(lin(e, tc, h, D, M, D, 3 * D, L.w_qkv, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, st));
+    if (fused) {
+      MTTS_TRY(layernorm_ex(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
+      MTTS_TRY(lin_planes(tc, Pa, M, D, 3 * D, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, nullptr, 0, st));
+    } else {
+      // h = LN1(x);  qkv = h Wqkv + b
+      MTTS_TRY(layernorm(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
+      MTTS_TRY(lin(e, tc, h, D, M, D, 3 * D, L.w_qkv, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, st));
+    }
     mtts_attn_params ap;
     memset(&ap, 0, sizeof(ap));
     ap.B = B; ap.H = H; ap.Tk = T; ap.dh = dh; ap.scale = scale;
@@ -102,6 +152,17 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
     ap.mask = mask; ap.mask_sb = mask_sb; ap.mask_sh = mask_sh; ap.mask_sq = mask_sq;
     if (!last) {
       ap.q = qkv; ap.q_sb = (int64_t)T * 3 * D; ap.q_st = 3 * D; ap.Tq = T;
+      if (fused) {
+        ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D;
+        MTTS_TRY(attention(ap, st));
+        MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st));
+        MTTS_TRY(layernorm_ex(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
+        // FF1: relu(h W1 + b1) goes straight to planes P_b; FF2 reads them
+        MTTS_TRY(lin_planes(tc, Pa, M, D, F, L.w_ff1_tc, L.b_ff1, nullptr, 0, nullptr, 0, MTTS_ACT_RELU, Pb, F, st));
+        MTTS_TRY(lin_planes(tc, Pb, M, F, D, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, nullptr, 0, st));
+        xin = xw;
+        continue;
+      }
       ap.o = a; ap.o_sb = (int64_t)T * D; ap.o_st = D;
       MTTS_TRY(attention(ap, st));
       // x = x + a Wo + bo

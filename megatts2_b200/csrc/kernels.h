@@ -1,8 +1,41 @@
 // Internal (C++) entry points shared by the drivers and the C ABI.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace mtts {
+// optional bf16x3 plane output of a producer kernel (feeds the tensor-core engine without a split pass)
+struct PlanesOut {
+  __nv_bfloat16* p;      // plane 0; planes 1, 2 follow at +stride, +2*stride (elements)
+  int64_t stride;
+  int ld;                // row stride (elements)
+  int act;               // activation applied to the planes copy (the consumer's pre-activation)
+  float slope;
+};
+
+// x = p0 + p1 + p2 to ~2^-24 (round-to-nearest at every step); 4 consecutive elements -> one 8-byte store per plane
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t plane_stride, int64_t off, const float* v) {
+  __nv_bfloat16 p[3][4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float a = v[e];
+    p[0][e] = __float2bfloat16_rn(a);
+    a -= __bfloat162float(p[0][e]);
+    p[1][e] = __float2bfloat16_rn(a);
+    a -= __bfloat162float(p[1][e]);
+    p[2][e] = __float2bfloat16_rn(a);
+  }
+#pragma unroll
+  for (int q = 0; q < 3; ++q) {
+    uint2 o;
+    o.x = (uint32_t)__bfloat16_as_ushort(p[q][0]) | ((uint32_t)__bfloat16_as_ushort(p[q][1]) << 16);
+    o.y = (uint32_t)__bfloat16_as_ushort(p[q][2]) | ((uint32_t)__bfloat16_as_ushort(p[q][3]) << 16);
+    *reinterpret_cast<uint2*>(planes + q * plane_stride + off) = o;
+  }
+}
+int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
+                 int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, PlanesOut po, cudaStream_t st);
 int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
 int conv1d(const mtts_conv_params& p, cudaStream_t st);   // engine dispatch (FFMA today)
 bool conv_tc_eligible(const mtts_conv_params& p);

@@ -4,7 +4,7 @@
 #include <float.h>
 #include <math.h>
 
-#include "common.cuh"
+#include "kernels.h"
 
 namespace mtts {
 
@@ -14,7 +14,7 @@ namespace mtts {
 __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* res, int ldr, float* y, int ldy, int64_t rows, int C, float eps,
-                 int post_act, int accumulate, int vec) {
+                 int post_act, int accumulate, int vec, const PlanesOut po) {
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -43,7 +43,7 @@ layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const
     }
   }
   const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
-  float* yr = y + row * ldy;
+  float* yr = y ? y + row * ldy : nullptr;
   const float* rr = res ? res + row * ldr : nullptr;
   if (vec) {
     for (int c = lane * 4; c < C; c += 128) {
@@ -62,33 +62,48 @@ layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const
         const float4 r = *reinterpret_cast<const float4*>(yr + c);
         o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
       }
-      *reinterpret_cast<float4*>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (yr) *reinterpret_cast<float4*>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
+      if (po.p) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], po.act, po.slope);
+        store_planes4(po.p, po.stride, row * po.ld + c, o);
+      }
     }
   } else {
     for (int c = lane; c < C; c += 32) {
       float o = act_apply((xr[c] - mean) * rstd * __ldg(gamma + c) + __ldg(beta + c), post_act, 0.f);
       if (rr) o += rr[c];
       if (accumulate) o += yr[c];
-      yr[c] = o;
+      if (yr) yr[c] = o;
     }
   }
 }
 
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
+int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr,
+                 float* y, int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, PlanesOut po,
+                 cudaStream_t st) {
+  MTTS_REQUIRE(x && gamma && beta && (y || po.p), "null pointer");
+  MTTS_REQUIRE(C > 0 && ldx >= C && (!y || ldy >= C), "bad dims");
+  MTTS_REQUIRE(!(accumulate && !y), "accumulate needs a y buffer");
+  if (rows <= 0) return 0;
+  const int vec = (C % 4 == 0) && (ldx % 4 == 0) && (!y || ((ldy % 4 == 0) && al16(y))) && al16(x) && al16(gamma) &&
+                  al16(beta) && (!res || ((ldr % 4 == 0) && al16(res)));
+  MTTS_REQUIRE(!po.p || (vec && po.ld % 4 == 0 && po.stride % 4 == 0), "plane output needs the vector path");
+  const int wpb = 8;
+  layernorm_kernel<<<(unsigned)cdiv64(rows, wpb), wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy,
+                                                                    rows, C, eps, post_act, accumulate, vec, po);
+  MTTS_CHECK_LAUNCH();
+  return 0;
+}
+
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr,
               float* y, int ldy, int64_t rows, int C, float eps, int post_act, int accumulate,
               cudaStream_t st) {
-  MTTS_REQUIRE(x && gamma && beta && y, "null pointer");
-  MTTS_REQUIRE(C > 0 && ldx >= C && ldy >= C, "bad dims");
-  if (rows <= 0) return 0;
-  const int vec = (C % 4 == 0) && (ldx % 4 == 0) && (ldy % 4 == 0) && al16(x) && al16(y) && al16(gamma) &&
-                  al16(beta) && (!res || ((ldr % 4 == 0) && al16(res)));
-  const int wpb = 8;
-  layernorm_kernel<<<(unsigned)cdiv64(rows, wpb), wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy,
-                                                                    rows, C, eps, post_act, accumulate, vec);
-  MTTS_CHECK_LAUNCH();
-  return 0;
+  MTTS_REQUIRE(y, "null pointer");
+  PlanesOut po{nullptr, 0, 0, 0, 0.f};
+  return layernorm_ex(x, ldx, gamma, beta, res, ldr, y, ldy, rows, C, eps, post_act, accumulate, po, st);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -208,14 +223,38 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
     }
     __syncwarp();
   }
+  if (p.o) {
 #pragma unroll
-  for (int i = 0; i < RW; ++i) {
-    const int qr = q0 + w * RW + i;
-    if (qr >= p.Tq) continue;
-    float* o = p.o + (int64_t)b * p.o_sb + (int64_t)qr * p.o_st + (int64_t)h * DH;
-    const float inv = 1.0f / l_run[i];
+    for (int i = 0; i < RW; ++i) {
+      const int qr = q0 + w * RW + i;
+      if (qr >= p.Tq) continue;
+      float* o = p.o + (int64_t)b * p.o_sb + (int64_t)qr * p.o_st + (int64_t)h * DH;
+      const float inv = 1.0f / l_run[i];
 #pragma unroll
-    for (int ii = 0; ii < NI; ++ii) o[lane + 32 * ii] = acc[i][ii] * inv;
+      for (int ii = 0; ii < NI; ++ii) o[lane + 32 * ii] = acc[i][ii] * inv;
+    }
+  }
+  if (p.o_planes) {
+    // bf16x3 planes for the following tensor-core GEMM: stage this warp's rows in its (now dead) Q rows so
+    // that every lane can split 4 CONSECUTIVE dims and store 8 bytes per plane
+    __syncwarp();
+    float* stg = Qs + (w * RW) * DH;
+#pragma unroll
+    for (int i = 0; i < RW; ++i) {
+      const float inv = 1.0f / l_run[i];
+#pragma unroll
+      for (int ii = 0; ii < NI; ++ii) stg[i * DH + lane + 32 * ii] = acc[i][ii] * inv;
+    }
+    __syncwarp();
+    __nv_bfloat16* pl = reinterpret_cast<__nv_bfloat16*>(p.o_planes);
+    for (int e = lane; e < RW * (DH / 4); e += 32) {
+      const int i = e / (DH / 4), d = (e - i * (DH / 4)) * 4;
+      const int qr = q0 + w * RW + i;
+      if (qr >= p.Tq) continue;
+      const float4 v = *reinterpret_cast<const float4*>(stg + i * DH + d);
+      const float vv[4] = {v.x, v.y, v.z, v.w};
+      store_planes4(pl, p.o_plane_stride, ((int64_t)b * p.Tq + qr) * p.o_planes_ld + (int64_t)h * DH + d, vv);
+    }
   }
 }
 
@@ -240,7 +279,8 @@ static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
 }
 
 int attention(const mtts_attn_params& p, cudaStream_t st) {
-  MTTS_REQUIRE(p.q && p.k && p.v && p.o, "null pointer");
+  MTTS_REQUIRE(p.q && p.k && p.v && (p.o || p.o_planes), "null pointer");
+  MTTS_REQUIRE(!p.o_planes || (p.o_planes_ld % 4 == 0 && p.o_plane_stride % 4 == 0), "plane output alignment");
   MTTS_REQUIRE(p.B >= 0 && p.H > 0 && p.Tq >= 0 && p.Tk > 0, "bad dims");
   MTTS_REQUIRE(p.H <= 65535 && p.B <= 65535, "grid too large");
   if (p.B == 0 || p.Tq == 0) return 0;
