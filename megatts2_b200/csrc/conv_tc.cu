@@ -37,14 +37,15 @@ struct ConvTcCfg {
   static constexpr int A_PLANE = 128 * SWB;
   static constexpr int B_PLANE = BN * SWB;
   static constexpr int STAGE = 3 * (A_PLANE + B_PLANE);
-  static constexpr int STAGES_RAW = (224 * 1024) / STAGE;
+  static constexpr int EPI_STAGE = 8 * 32 * 20 * 4;          // epilogue transpose buffers: 8 warps x [32 rows][20 floats]
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256;
+  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + EPI_STAGE;
   static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;   // 2 buffers x (main + correction) x BN
 };
 
 template <int BN, int SWB>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(384, 1)
 conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
   using Cfg = ConvTcCfg<BN, SWB>;
   constexpr int STAGES = Cfg::STAGES;
@@ -55,6 +56,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  float* epi_stage = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_t = (g.T + 127) / 128, num_n = (g.Cout + BN - 1) / BN;
@@ -76,7 +78,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 4);
+      mbar_init(tempty_bar + 8 * s, 8);     // one arrive per epilogue warp (8 warps)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -150,8 +152,12 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
       }
     }
   } else if (warp >= 4) {
-    // ================= epilogue =================
-    const int q = warp - 4;
+    // ================= epilogue: 8 warps, two per TMEM lane quarter, 16-column units =================
+    // (the small-channel convs are epilogue-bound: per output element there is more CUDA-core work than
+    //  tensor-pipe work, so the epilogue gets as many warps as the register file allows)
+    const int ew = warp - 4;                      // 0..7
+    const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
+    const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
       const int nb = tile % num_n, r0 = tile / num_n;
@@ -159,61 +165,66 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
       const int as = it & 1, aphase = (it >> 1) & 1;
       mbar_wait(tfull_bar + 8 * as, aphase);
       tc_fence_after();
-      const int t = tb * 128 + q * 32 + lane;
+      // Each unit = this warp's 32 rows x 16 columns.  The accumulators arrive row-per-lane (TMEM lane == row);
+      // writing them out like that would make every global instruction touch 32 different lines, so the unit
+      // is transposed through a padded shared buffer and ALL global traffic of the epilogue (y, residual,
+      // accumulate, bf16 planes) is issued as 8 rows x 64 contiguous bytes per instruction.
+      float* stg = epi_stage + ew * (32 * 20);
+      const int chunk = lane & 3, rsub = lane >> 2;
+      const int t_base = tb * 128 + q * 32;
 #pragma unroll 1
-      for (int c = 0; c < BN / 32; ++c) {
-        const int n0 = nb * BN + c * 32;
-        const bool live = (t < g.T) && (n0 < g.Cout);
-        const bool full = live && (n0 + 32 <= g.Cout);
-        float* yr = g.y ? g.y + (int64_t)b * g.y_sb + (int64_t)t * g.ldy + n0 : nullptr;
-        const float* rr = g.res ? g.res + (int64_t)b * g.res_sb + (int64_t)t * g.ldr + n0 : nullptr;
-        // All global operands of this chunk are fetched as INDEPENDENT float4 loads before the TMEM read:
-        // a per-element `x += __ldg(bias)` chain costs one exposed L2 round trip per element and was the
-        // bottleneck of the small-channel convs (ncu: long-scoreboard stalls on 64-128 dependent loads per tile).
-        float4 bv[8], rv[8], ov[8];
-        if (full) {
+      for (int u = half; u < BN / 16; u += 2) {
+        const int n = nb * BN + u * 16 + chunk * 4;
+        const bool ncol = n < g.Cout;                 // Cout % 4 == 0: a 4-wide chunk is all-in or all-out
+        // independent global loads first (bias once per lane; residual / accumulate per owned row)
+        float4 bvec = make_float4(0.f, 0.f, 0.f, 0.f), rv[4], ov[4];
+        if (ncol && g.bias) bvec = __ldg(reinterpret_cast<const float4*>(g.bias + n));
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            bv[j] = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n0) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            rv[j] = rr ? *(reinterpret_cast<const float4*>(rr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-            ov[j] = g.accumulate ? *(reinterpret_cast<const float4*>(yr) + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int i = 0; i < 4; ++i) {
+          const int tt = t_base + i * 8 + rsub;
+          rv[i] = ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ncol && tt < g.T) {
+            if (g.res) rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
+            if (g.accumulate) ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
           }
         }
-        uint32_t r[32], rc[32];
-        const uint32_t ta = tmem_base + as * (2 * BN) + c * 32 + ((uint32_t)(q * 32) << 16);
-        tmem_ld32(ta, r);
-        tmem_ld32(ta + BN, rc);
-        if (full) {
+        uint32_t r[16], rc[16];
+        const uint32_t ta = tmem_base + as * (2 * BN) + u * 16 + ((uint32_t)(q * 32) << 16);
+        tmem_ld16(ta, r);
+        tmem_ld16(ta + BN, rc);
+        tmem_ld_wait();
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float v0 = __uint_as_float(r[4 * j + 0]) + __uint_as_float(rc[4 * j + 0]) + bv[j].x;
-            float v1 = __uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1]) + bv[j].y;
-            float v2 = __uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2]) + bv[j].z;
-            float v3 = __uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3]) + bv[j].w;
-            v0 = act_apply(v0, g.post_act, 0.f); v1 = act_apply(v1, g.post_act, 0.f);
-            v2 = act_apply(v2, g.post_act, 0.f); v3 = act_apply(v3, g.post_act, 0.f);
-            v0 = (v0 + rv[j].x) * g.out_scale + ov[j].x;
-            v1 = (v1 + rv[j].y) * g.out_scale + ov[j].y;
-            v2 = (v2 + rv[j].z) * g.out_scale + ov[j].z;
-            v3 = (v3 + rv[j].w) * g.out_scale + ov[j].w;
-            if (yr) *(reinterpret_cast<float4*>(yr) + j) = make_float4(v0, v1, v2, v3);
-            if (g.op) {
-              const float pv[4] = {act_apply(v0, g.op_act, g.op_slope), act_apply(v1, g.op_act, g.op_slope),
-                                   act_apply(v2, g.op_act, g.op_slope), act_apply(v3, g.op_act, g.op_slope)};
-              store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + t) * g.op_ld + n0 + 4 * j, pv);
+        for (int j = 0; j < 4; ++j)
+          *reinterpret_cast<float4*>(stg + lane * 20 + 4 * j) =
+              make_float4(__uint_as_float(r[4 * j + 0]) + __uint_as_float(rc[4 * j + 0]),
+                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1]),
+                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2]),
+                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3]));
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = i * 8 + rsub, tt = t_base + row;
+          if (!ncol || tt >= g.T) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 20 + chunk * 4);
+          float v[4] = {a4.x + bvec.x, a4.y + bvec.y, a4.z + bvec.z, a4.w + bvec.w};
+          if (g.post_act != MTTS_ACT_NONE) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, 0.f);
+          }
+          v[0] = (v[0] + rv[i].x) * g.out_scale + ov[i].x;
+          v[1] = (v[1] + rv[i].y) * g.out_scale + ov[i].y;
+          v[2] = (v[2] + rv[i].z) * g.out_scale + ov[i].z;
+          v[3] = (v[3] + rv[i].w) * g.out_scale + ov[i].w;
+          if (g.y) *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.op) {
+            if (g.op_act != MTTS_ACT_NONE) {
+#pragma unroll
+              for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.op_act, g.op_slope);
             }
-          }
-        } else if (live) {
-          for (int j = 0; j < 32 && n0 + j < g.Cout; ++j) {
-            float x = __uint_as_float(r[j]) + __uint_as_float(rc[j]);
-            if (g.bias) x += __ldg(g.bias + n0 + j);
-            x = act_apply(x, g.post_act, 0.f);
-            if (rr) x += rr[j];
-            x *= g.out_scale;
-            if (g.accumulate) x += yr[j];
-            if (yr) yr[j] = x;
+            store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v);
           }
         }
+        __syncwarp();   // the staging buffer is reused by the next unit
       }
       tc_fence_before();
       __syncwarp();
@@ -273,6 +284,43 @@ split_pad_bf16x3_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int 
     o.y = (uint32_t)__bfloat16_as_ushort(p[qn][2]) | ((uint32_t)__bfloat16_as_ushort(p[qn][3]) << 16);
     *reinterpret_cast<uint2*>(planes + qn * plane_stride + off) = o;
   }
+}
+
+// Materialise the padding rows of plane buffers whose interior rows were written by a producer epilogue:
+// planes (3, B, Tp, C) bf16 with hl leading halo rows; reflect / replicate / zero about the T interior rows.
+__global__ void __launch_bounds__(256)
+halo_fill_kernel(__nv_bfloat16* __restrict__ planes, int64_t plane_stride, int T, int C, int hl, int Tp, int pad_mode) {
+  const int b = blockIdx.y, q = blockIdx.z;
+  const int nh = Tp - T;                     // halo rows in total (hl leading, the rest trailing)
+  const int c8 = C / 8;                      // 16-byte chunks per row
+  __nv_bfloat16* base = planes + q * plane_stride + (int64_t)b * Tp * C;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < nh * c8; i += gridDim.x * blockDim.x) {
+    const int hr = i / c8, ch = i - hr * c8;
+    const int u = hr < hl ? hr : T + hr;     // padded row index of this halo row
+    int ti = u - hl;
+    if (pad_mode == MTTS_PAD_REPLICATE) ti = ti < 0 ? 0 : T - 1;
+    else if (pad_mode == MTTS_PAD_REFLECT) {
+      if (ti < 0) ti = -ti;
+      if (ti >= T) ti = 2 * (T - 1) - ti;
+      if (ti < 0 || ti >= T) ti = -1;
+    } else ti = -1;
+    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+    if (ti >= 0) v = *reinterpret_cast<const uint4*>(base + (int64_t)(hl + ti) * C + ch * 8);
+    *reinterpret_cast<uint4*>(base + (int64_t)u * C + ch * 8) = v;
+  }
+}
+
+int halo_fill(void* planes_base, int B, int T, int C, int hl, int hr, int pad_mode, cudaStream_t st) {
+  MTTS_REQUIRE(planes_base && C % 8 == 0 && hl >= 0 && hr >= 0, "bad arguments");
+  if (hl + hr == 0 || B <= 0) return 0;
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)planes_base) + 1023) & ~(uintptr_t)1023);
+  const int Tp = T + hl + hr;
+  const int64_t plane_stride = (int64_t)B * Tp * C;
+  const int work = (hl + hr) * (C / 8);
+  dim3 grid((unsigned)cdiv64(work, 256), (unsigned)B, 3);
+  halo_fill_kernel<<<grid, 256, 0, st>>>(planes, plane_stride, T, C, hl, Tp, pad_mode);
+  MTTS_CHECK_LAUNCH();
+  return 0;
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -345,7 +393,7 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
   }
   const int64_t tiles = (int64_t)a.B * cdiv64(a.T, 128) * cdiv64(a.Cout, BN);
   const int grid = (int)(tiles < g_ctc_sms ? tiles : g_ctc_sms);
-  conv_bf16x3_kernel<BN, SWB><<<grid, 256, Cfg::SMEM, st>>>(maps, a);
+  conv_bf16x3_kernel<BN, SWB><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
   MTTS_CHECK_LAUNCH();
   return 0;
 }

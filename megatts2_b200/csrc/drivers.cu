@@ -447,7 +447,7 @@ static int64_t hifigan_ws_floats(const mtts_hifigan* h, int B, int T) {
     if (L * C > big) big = L * C;
   }
   const int64_t tcb = h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0;   // + halo rows
-  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + tcb / 4 + 64;
+  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + 2 * (tcb / 4 + 64);
 }
 
 static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int mel_ld, int B, int T, float* wav,
@@ -468,8 +468,15 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
   float* bufs[5];
   for (int i = 0; i < 5; ++i) bufs[i] = ar.take<float>((int64_t)B * big);
   ConvTc tc{h->engine, nullptr, h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0};
-  if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
+  char* planes2 = nullptr;                      // second plane buffer for the fused ResBlock flow
+  if (tc.bytes) {
+    tc.scratch = ar.take<char>(tc.bytes);
+    planes2 = ar.take<char>(tc.bytes);
+  }
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "hifigan", ar.off);
+  bool fused = h->engine == 1 && tc.scratch && planes2;
+  for (int n = 0; fused && n < h->n_ups * h->n_kernels; ++n)
+    for (int m = 0; m < 3; ++m) fused = fused && h->resblocks[n].w1_tc[m] && h->resblocks[n].w2_tc[m];
   // replicate-pad `pad` frames at both ends (HifiganGenerator.inference)
   MTTS_TRY(copy_strided(mel, mel_sb, mel_ld, 1, mp, (int64_t)Tp * h->in_channels, h->in_channels, 1, B, T,
                         h->in_channels, pad, st));
@@ -503,6 +510,48 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
     }
     for (int j = 0; j < h->n_kernels; ++j) {
       const mtts_hifigan_resblock& rb = h->resblocks[i * h->n_kernels + j];
+      const bool fuse_rb = fused && (Co == 32 || Co == 64 || (Co >= 128 && Co % 32 == 0)) && (int64_t)B * Lo >= 128;
+      if (fuse_rb) {
+        // Fused plane flow: only the ResBlock input is split by a standalone pass; every conv epilogue writes
+        // the NEXT conv's input planes (leaky applied, interior rows), halo_fill materialises the reflect padding.
+        const int h2 = (rb.k - 1) / 2;
+        const float* xcur = oup;
+        for (int m = 0; m < 3; ++m) {
+          const int h1 = rb.dil[m] * (rb.k - 1) / 2;
+          mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], nullptr, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);
+          c1.pre_act = MTTS_ACT_LEAKY; c1.pre_slope = 0.1f;
+          c1.w_tc = rb.w1_tc[m]; c1.tc_scratch = tc.scratch; c1.tc_scratch_bytes = tc.bytes;
+          c1.tc_presplit = (m > 0);              // m == 0: split_pad(leaky(oup)) runs inside conv_tc
+          c1.y = nullptr;
+          c1.tc_out_planes = reinterpret_cast<void*>((((uintptr_t)planes2) + 1023) & ~(uintptr_t)1023);
+          c1.tc_out_tp = Lo + 2 * h2; c1.tc_out_hl = h2; c1.tc_out_ld = Co;
+          c1.tc_out_plane_stride = (int64_t)B * c1.tc_out_tp * Co;
+          c1.tc_out_act = MTTS_ACT_LEAKY; c1.tc_out_slope = 0.1f;
+          if (!conv_tc_eligible(c1)) return fail(MTTS_ERR_UNSUPPORTED, "%s: fused ResBlock conv not eligible (C=%lld L=%lld)", "hifigan", Co, Lo);
+          MTTS_TRY(conv1d(c1, st));
+          MTTS_TRY(halo_fill(planes2, B, Lo, Co, h2, h2, MTTS_PAD_REFLECT, st));
+          const bool lastm = (m == 2);
+          mtts_conv_params c2 = conv_same_params(nullptr, rb.w2[m], rb.b2[m], lastm ? z : xr, B, Lo, Co, Co, rb.k, 1, MTTS_PAD_REFLECT);
+          c2.w_tc = rb.w2_tc[m]; c2.tc_scratch = planes2; c2.tc_scratch_bytes = tc.bytes; c2.tc_presplit = 1;
+          c2.res = xcur; c2.res_batch_stride = (int64_t)Lo * Co; c2.ldr = Co;
+          if (lastm) {
+            c2.out_scale = 1.0f / (float)h->n_kernels;
+            c2.accumulate = (j > 0);
+          } else {
+            const int h1n = rb.dil[m + 1] * (rb.k - 1) / 2;
+            c2.tc_out_planes = reinterpret_cast<void*>((((uintptr_t)tc.scratch) + 1023) & ~(uintptr_t)1023);
+            c2.tc_out_tp = Lo + 2 * h1n; c2.tc_out_hl = h1n; c2.tc_out_ld = Co;
+            c2.tc_out_plane_stride = (int64_t)B * c2.tc_out_tp * Co;
+            c2.tc_out_act = MTTS_ACT_LEAKY; c2.tc_out_slope = 0.1f;
+          }
+          if (!conv_tc_eligible(c2)) return fail(MTTS_ERR_UNSUPPORTED, "%s: fused ResBlock conv not eligible (C=%lld L=%lld)", "hifigan", Co, Lo);
+          MTTS_TRY(conv1d(c2, st));
+          if (!lastm) MTTS_TRY(halo_fill(tc.scratch, B, Lo, Co, rb.dil[m + 1] * (rb.k - 1) / 2, rb.dil[m + 1] * (rb.k - 1) / 2, MTTS_PAD_REFLECT, st));
+          (void)h1;
+          xcur = xr;
+        }
+        continue;
+      }
       const float* xcur = oup;
       for (int m = 0; m < 3; ++m) {
         mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], xt, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);

@@ -40,6 +40,7 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
 int conv1d(const mtts_conv_params& p, cudaStream_t st);   // engine dispatch (FFMA today)
 bool conv_tc_eligible(const mtts_conv_params& p);
 int conv_tc(const mtts_conv_params& p, cudaStream_t st);
+int halo_fill(void* planes_base, int B, int T, int C, int hl, int hr, int pad_mode, cudaStream_t st);
 int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K);
 int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,
               const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,

@@ -252,6 +252,45 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
 
 
 
+// Single-output-channel conv (HiFi-GAN conv_post: 32 -> 1, k = 7, tanh).  One thread per output sample walks
+// its k x Cin window with float4 loads (neighbouring threads share rows through L1); weights sit in shared
+// memory.  A 128x32 GEMM tile would waste 31/32 of its columns here.
+__global__ void __launch_bounds__(256)
+conv_cout1_kernel(const mtts_conv_params p) {
+  extern __shared__ __align__(16) float wsm[];       // [k][Cin]
+  for (int i = threadIdx.x; i < p.k * p.Cin; i += 256) wsm[i] = __ldg(p.w + i);   // packed (k, Cin, 1)
+  __syncthreads();
+  const int64_t M = (int64_t)p.B * p.Tout;
+  const int64_t m = (int64_t)blockIdx.x * 256 + threadIdx.x;
+  if (m >= M) return;
+  const int b = (int)(m / p.Tout), t = (int)(m - (int64_t)b * p.Tout);
+  const int len = p.in_lens ? min(p.in_lens[b], p.Tin) : p.Tin;
+  const float* xb = p.x + (int64_t)b * p.x_batch_stride;
+  float acc = 0.f;
+  for (int j = 0; j < p.k; ++j) {
+    const int ti = map_row(t * p.stride + j * p.dil - p.pad, len, p.pad_mode);
+    if (ti < 0) continue;
+    const float4* xr = reinterpret_cast<const float4*>(xb + (int64_t)ti * p.ldx);
+    const float4* wr = reinterpret_cast<const float4*>(wsm + j * p.Cin);
+    for (int c = 0; c < p.Cin / 4; ++c) {
+      float4 v = __ldg(xr + c);
+      const float4 w = wr[c];
+      if (p.pre_act != MTTS_ACT_NONE) {
+        v.x = act_apply(v.x, p.pre_act, p.pre_slope); v.y = act_apply(v.y, p.pre_act, p.pre_slope);
+        v.z = act_apply(v.z, p.pre_act, p.pre_slope); v.w = act_apply(v.w, p.pre_act, p.pre_slope);
+      }
+      acc = fmaf(v.x, w.x, acc); acc = fmaf(v.y, w.y, acc); acc = fmaf(v.z, w.z, acc); acc = fmaf(v.w, w.w, acc);
+    }
+  }
+  if (p.bias) acc += __ldg(p.bias);
+  acc = act_apply(acc, p.post_act, p.post_slope);
+  if (p.res) acc += p.res[(int64_t)b * p.res_batch_stride + (int64_t)t * p.ldr];
+  acc *= p.out_scale;
+  float* dst = p.y + (int64_t)b * p.y_batch_stride + (int64_t)t * p.ldy;
+  if (p.accumulate) acc += *dst;
+  *dst = acc;
+}
+
 // split-K second pass: fixed-order sum of the partials (deterministic), then the usual epilogue
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const mtts_conv_params p, const float* __restrict__ partial, int splits) {
@@ -300,6 +339,11 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st) {
   fl.vec_y = (p.Cout % 4 == 0) && (p.ldy % 4 == 0) && (p.y_batch_stride % 4 == 0) && al16(p.y) &&
              (p.out_shift % 4 == 0) && (p.y_batch_elems % 4 == 0) &&
              (!p.res || ((p.ldr % 4 == 0) && (p.res_batch_stride % 4 == 0) && al16(p.res)));
+  if (p.Cout == 1 && p.out_shift == 0 && fl.vec_a && p.k * p.Cin <= 8192 && M >= 4096) {
+    conv_cout1_kernel<<<(unsigned)cdiv64(M, 256), 256, (size_t)p.k * p.Cin * sizeof(float), st>>>(p);
+    MTTS_CHECK_LAUNCH();
+    return 0;
+  }
   // Small-M linear layers (the last-position GEMMs of the AR loops: M = batch rows): a 64x64 tile grid leaves
   // most SMs idle and every CTA walks all of K serially.  Split K over blockIdx.z into the caller's scratch and
   // reduce in a fixed order (bit-reproducible), so ~all SMs stream a slice of the weights.

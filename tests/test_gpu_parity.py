@@ -57,6 +57,7 @@ CONV_CASES = [
     dict(B=2, T=125, Cin=20, Cout=384, k=5),                                     # Cin % 16 != 0
     dict(B=2, T=131, Cin=512, Cout=80, k=5),                                     # Cout = 80
     dict(B=3, T=257, Cin=32, Cout=1, k=7, pad_mode=1, pre=2, post=3),            # conv_post: reflect, leaky, tanh
+    dict(B=2, T=5000, Cin=32, Cout=1, k=7, pad_mode=1, pre=2, post=3),           # conv_post, single-channel kernel
     dict(B=2, T=500, Cin=512, Cout=512, k=17, stride=16, pad=8),                 # MRTE strided conv
     dict(B=2, T=200, Cin=64, Cout=64, k=11, dil=5, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),
     dict(B=2, T=333, Cin=32, Cout=32, k=3, dil=3, pad_mode=1, pre=2),            # 128x32 tiles
