@@ -290,6 +290,7 @@ typedef struct {
   int32_t up_factor[4], up_kernel[4];
   const float *w_pre, *b_pre;          /* packed (7, 80, ch0) */
   const float *w_up[4], *b_up[4];      /* packed (2, Cin, s*Cout), bias expanded to (s*Cout) */
+  const void* w_up_tc[4];              /* (3, 2, s*Cout, Cin) bf16 planes or NULL */
   const mtts_hifigan_resblock* resblocks;  /* HOST array [n_ups*n_kernels] */
   const float *w_post, *b_post;        /* packed (7, C_last, 1) */
 } mtts_hifigan;

@@ -95,7 +95,7 @@ class HifiganResblock(C.Structure):
 class Hifigan(C.Structure):
     _fields_ = [("in_channels", i32), ("ch0", i32), ("n_ups", i32), ("n_kernels", i32), ("inference_padding", i32),
                 ("engine", i32), ("up_factor", i32 * 4), ("up_kernel", i32 * 4), ("w_pre", vp), ("b_pre", vp),
-                ("w_up", vp * 4), ("b_up", vp * 4), ("resblocks", C.POINTER(HifiganResblock)),
+                ("w_up", vp * 4), ("b_up", vp * 4), ("w_up_tc", vp * 4), ("resblocks", C.POINTER(HifiganResblock)),
                 ("w_post", vp), ("b_post", vp)]
 
 

@@ -27,6 +27,7 @@ struct ConvTcArgs {
   const float* res; int64_t res_sb; int32_t ldr;
   float* y; int64_t y_sb; int32_t ldy;
   int32_t post_act; float out_scale; int32_t accumulate;
+  int64_t out_shift, ybe;      // transposed-conv form: element offset of the output and valid range per batch item
   // optional bf16x3 copy of the result for the next tensor-core layer
   __nv_bfloat16* op; int64_t op_stride; int32_t op_ld, op_tp, op_hl, op_act; float op_slope;
 };
@@ -93,25 +94,24 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    if (lane == 0) {   // ================= TMA producer =================
-      int stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int nb = tile % num_n, r = tile / num_n;
-        const int tb = r % num_t, b = r / num_t;
-        for (int kb = 0; kb < num_k; ++kb) {
-          const int j = kb / ncb, cb = kb - j * ncb;
-          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-          const uint32_t fb = full_bar + 8 * stage;
-          mbar_expect_tx(fb, Cfg::STAGE);
-          const uint32_t sa = smem_base + stage * Cfg::STAGE;
-          const uint32_t sb = sa + 3 * Cfg::A_PLANE;
-#pragma unroll
-          for (int p = 0; p < 3; ++p) {
-            tma_load_3d(sa + p * Cfg::A_PLANE, &maps.a[p], fb, cb * Cfg::BK, tb * 128 + j * g.dil, b);
-            tma_load_2d(sb + p * Cfg::B_PLANE, &maps.b[p], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
+    // ================= TMA producer: the whole warp walks the pipeline; lanes 0..5 each issue ONE of the six
+    // bulk copies of a K-slab (A p0..p2, B p0..p2) so the copies are issued concurrently - with one issuing
+    // thread the ~6 x 100-150 cycles of issue latency per slab bound the small-channel convs
+    int stage = 0, phase = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int nb = tile % num_n, r = tile / num_n;
+      const int tb = r % num_t, b = r / num_t;
+      for (int kb = 0; kb < num_k; ++kb) {
+        const int j = kb / ncb, cb = kb - j * ncb;
+        mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+        const uint32_t fb = full_bar + 8 * stage;
+        if (lane == 0) mbar_expect_tx(fb, Cfg::STAGE);
+        __syncwarp();
+        const uint32_t sa = smem_base + stage * Cfg::STAGE;
+        const uint32_t sb = sa + 3 * Cfg::A_PLANE;
+        if (lane < 3) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, tb * 128 + j * g.dil, b);
+        else if (lane < 6) tma_load_2d(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
@@ -183,7 +183,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
         for (int i = 0; i < 4; ++i) {
           const int tt = t_base + i * 8 + rsub;
           rv[i] = ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ncol && tt < g.T) {
+          if (ncol && tt < g.T && !g.out_shift) {
             if (g.res) rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
             if (g.accumulate) ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
           }
@@ -215,7 +215,11 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
           v[1] = (v[1] + rv[i].y) * g.out_scale + ov[i].y;
           v[2] = (v[2] + rv[i].z) * g.out_scale + ov[i].z;
           v[3] = (v[3] + rv[i].w) * g.out_scale + ov[i].w;
-          if (g.y) *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+          if (g.y) {
+            const int64_t flat = (int64_t)tt * g.ldy + n + g.out_shift;     // out_shift % 4 == 0: all-in or all-out
+            if (flat >= 0 && flat + 4 <= g.ybe)
+              *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + flat) = make_float4(v[0], v[1], v[2], v[3]);
+          }
           if (g.op) {
             if (g.op_act != MTTS_ACT_NONE) {
 #pragma unroll
@@ -400,7 +404,9 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
 
 bool conv_tc_eligible(const mtts_conv_params& p) {
   if (!p.w_tc || !p.tc_scratch) return false;
-  if (p.stride != 1 || p.out_shift != 0 || p.in_lens) return false;
+  if (p.stride != 1 || p.in_lens) return false;
+  if (p.out_shift != 0 && (p.out_shift % 4 != 0 || p.y_batch_elems % 4 != 0 || p.res || p.accumulate || p.tc_out_planes || !p.y))
+    return false;
   if (p.Cin % 8 != 0 || p.Cin < 32) return false;
   if (!p.tc_presplit && (p.ldx % 4 != 0 || (p.x_batch_stride % 4) != 0 || (((uintptr_t)p.x) & 15) != 0)) return false;
   if (!(p.Cout == 32 || p.Cout == 64 || (p.Cout >= 128 && p.Cout % 32 == 0))) return false;
@@ -459,6 +465,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.bias = p.bias; a.res = p.res; a.res_sb = p.res_batch_stride; a.ldr = p.ldr;
   a.y = p.y; a.y_sb = p.y_batch_stride; a.ldy = p.ldy;
   a.post_act = p.post_act; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
+  a.out_shift = p.out_shift; a.ybe = p.y_batch_elems ? p.y_batch_elems : (int64_t)p.Tout * p.ldy;
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   if (SWB == 64) return conv_tc_launch<32, 64>(maps, a, st);

@@ -506,6 +506,7 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
       p.out_scale = 1.0f;
       p.out_shift = -(int64_t)pt * Co;
       p.y_batch_elems = (int64_t)Lo * Co;
+      attach_tc(p, h->w_up_tc[i], &tc);
       MTTS_TRY(conv1d(p, st));
     }
     for (int j = 0; j < h->n_kernels; ++j) {

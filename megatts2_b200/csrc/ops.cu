@@ -79,6 +79,60 @@ layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const
   }
 }
 
+// Register-resident variant for the row widths of the path (C = 128*NV, NV float4 per lane): one global read
+// of the row (NV independent 128-bit loads in flight), two shuffle reductions, one write.
+template <int NV>
+__global__ void __launch_bounds__(256)
+layernorm_reg_kernel(const float* x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
+                     const float* res, int ldr, float* y, int ldy, int64_t rows, float eps, int post_act,
+                     int accumulate, const PlanesOut po) {
+  constexpr int C = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const float* xr = x + row * ldx;
+  float4 v[NV];
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(xr + i * 128 + lane * 4);
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + b * b) + (d * d + e * e);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+  float* yr = y ? y + row * ldy : nullptr;
+  const float* rr = res ? res + row * ldr : nullptr;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o[4] = {(v[i].x - mean) * rstd * g.x + bb.x, (v[i].y - mean) * rstd * g.y + bb.y,
+                  (v[i].z - mean) * rstd * g.z + bb.z, (v[i].w - mean) * rstd * g.w + bb.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], post_act, 0.f);
+    if (rr) {
+      const float4 r = *reinterpret_cast<const float4*>(rr + c);
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    if (accumulate) {
+      const float4 r = *reinterpret_cast<const float4*>(yr + c);
+      o[0] += r.x; o[1] += r.y; o[2] += r.z; o[3] += r.w;
+    }
+    if (yr) *reinterpret_cast<float4*>(yr + c) = make_float4(o[0], o[1], o[2], o[3]);
+    if (po.p) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], po.act, po.slope);
+      store_planes4(po.p, po.stride, row * po.ld + c, o);
+    }
+  }
+}
+
 static inline bool al16(const void* p) { return (((uintptr_t)p) & 15) == 0; }
 
 int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr,
@@ -92,8 +146,18 @@ int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta,
                   al16(beta) && (!res || ((ldr % 4 == 0) && al16(res)));
   MTTS_REQUIRE(!po.p || (vec && po.ld % 4 == 0 && po.stride % 4 == 0), "plane output needs the vector path");
   const int wpb = 8;
-  layernorm_kernel<<<(unsigned)cdiv64(rows, wpb), wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy,
-                                                                    rows, C, eps, post_act, accumulate, vec, po);
+  const unsigned grid = (unsigned)cdiv64(rows, wpb);
+#define MTTS_LN_REG(NV)                                                                                          \
+  layernorm_reg_kernel<NV><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy, rows, eps, post_act, \
+                                                      accumulate, po)
+  if (vec && C == 1024) MTTS_LN_REG(8);
+  else if (vec && C == 768) MTTS_LN_REG(6);
+  else if (vec && C == 512) MTTS_LN_REG(4);
+  else if (vec && C == 384) MTTS_LN_REG(3);
+  else
+    layernorm_kernel<<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy, rows, C, eps, post_act,
+                                                accumulate, vec, po);
+#undef MTTS_LN_REG
   MTTS_CHECK_LAUNCH();
   return 0;
 }

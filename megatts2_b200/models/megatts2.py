@@ -289,6 +289,11 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
                 s.up_factor[i], s.up_kernel[i] = u, k
                 wp, bp = pack.pack_conv_transpose(self.ups[i].weight, self.ups[i].bias, u)
                 s.w_up[i], s.b_up[i] = pl.p(wp), pl.p(bp)
+                if engine == 1:     # (2, Cin, s*Cout) fp32 -> (3, 2, s*Cout, Cin) bf16 planes
+                    tup = pack.pack_tc_planes(wp.permute(0, 2, 1).reshape(-1, wp.shape[1])).reshape(
+                        3, 2, wp.shape[2], wp.shape[1]).contiguous()
+                    pl.keep.append(tup)
+                    s.w_up_tc[i] = tup.data_ptr()
             arr = (L.HifiganResblock * len(self.resblocks))()
             for n, rb in enumerate(self.resblocks):
                 j = n % s.n_kernels
