@@ -11,6 +11,8 @@
 #include <mutex>
 #include <unordered_map>
 
+#include <stdlib.h>
+
 #include "kernels.h"
 #include "tc_ptx.cuh"
 
@@ -32,24 +34,33 @@ struct ConvTcArgs {
   __nv_bfloat16* op; int64_t op_stride; int32_t op_ld, op_tp, op_hl, op_act; float op_slope;
 };
 
-template <int BN, int SWB>
+// PAIR = 1: two CTAs of a cluster run one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of
+// the activations and HALF of the weight tile, so the L2 -> SM traffic per FLOP drops by a quarter
+template <int BN, int SWB, int PAIR = 0>
 struct ConvTcCfg {
   static constexpr int BK = SWB / 2;                       // bf16 elements per swizzled row
   static constexpr int A_PLANE = 128 * SWB;
-  static constexpr int B_PLANE = BN * SWB;
+  static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by one CTA
+  static constexpr int B_PLANE = B_ROWS * SWB;
   static constexpr int STAGE = 3 * (A_PLANE + B_PLANE);
   static constexpr int EPI_STAGE = 8 * 32 * 20 * 4;          // epilogue transpose buffers: 8 warps x [32 rows][20 floats]
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + EPI_STAGE;
-  static constexpr int TMEM_COLS = 4 * BN < 32 ? 32 : 4 * BN;   // 2 buffers x (main + correction) x BN
+  static constexpr int NACC = (4 * BN > 512) ? 1 : 2;            // accumulator buffers: BN = 256 fills TMEM with one
+  static constexpr int TMEM_COLS = NACC * 2 * BN < 32 ? 32 : NACC * 2 * BN;   // NACC x (main + correction) x BN
 };
 
-template <int BN, int SWB>
+template <int BN, int SWB, int PAIR>
 __global__ void __launch_bounds__(384, 1)
 conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
-  using Cfg = ConvTcCfg<BN, SWB>;
+  using Cfg = ConvTcCfg<BN, SWB, PAIR>;
+  constexpr int BM = PAIR ? 256 : 128;                     // rows of one (pair) tile
+  const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
+  const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a CTA or a CTA pair)
+  const int nworkers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const uint32_t bars = smem_base + STAGES * Cfg::STAGE;
@@ -60,7 +71,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
   float* epi_stage = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // 16-byte aligned
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int num_t = (g.T + 127) / 128, num_n = (g.Cout + BN - 1) / BN;
+  const int num_t = (g.T + BM - 1) / BM, num_n = (g.Cout + BN - 1) / BN;
   const int num_tiles = g.B * num_t * num_n;
   const int ncb = (g.Cin + Cfg::BK - 1) / Cfg::BK;
   const int num_k = g.k * ncb;
@@ -79,17 +90,24 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
-      mbar_init(tempty_bar + 8 * s, 8);     // one arrive per epilogue warp (8 warps)
+      mbar_init(tempty_bar + 8 * s, PAIR ? 16 : 8);     // one arrive per epilogue warp (8 warps per CTA)
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 2) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if constexpr (PAIR) {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
@@ -98,55 +116,80 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     // bulk copies of a K-slab (A p0..p2, B p0..p2) so the copies are issued concurrently - with one issuing
     // thread the ~6 x 100-150 cycles of issue latency per slab bound the small-channel convs
     int stage = 0, phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    for (int tile = worker; tile < num_tiles; tile += nworkers) {
       const int nb = tile % num_n, r = tile / num_n;
       const int tb = r % num_t, b = r / num_t;
+      const int trow = tb * BM + (int)crank * 128;               // this CTA's first output row
       for (int kb = 0; kb < num_k; ++kb) {
         const int j = kb / ncb, cb = kb - j * ncb;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
-        const uint32_t fb = full_bar + 8 * stage;
-        if (lane == 0) mbar_expect_tx(fb, Cfg::STAGE);
-        __syncwarp();
         const uint32_t sa = smem_base + stage * Cfg::STAGE;
         const uint32_t sb = sa + 3 * Cfg::A_PLANE;
-        if (lane < 3) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, tb * 128 + j * g.dil, b);
-        else if (lane < 6) tma_load_2d(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+        if constexpr (PAIR) {
+          // both CTAs' bytes are counted on the LEADER's barrier (the leader issues the MMAs for the pair)
+          const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);
+          if (lane == 0 && crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE);
+          __syncwarp();
+          if (lane < 3) tma_load_3d_2sm(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
+          else if (lane < 6)
+            tma_load_2d_2sm(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK,
+                            j * g.Cout + nb * BN + (int)crank * Cfg::B_ROWS);
+        } else {
+          const uint32_t fb = full_bar + 8 * stage;
+          if (lane == 0) mbar_expect_tx(fb, Cfg::STAGE);
+          __syncwarp();
+          if (lane < 3) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
+          else if (lane < 6) tma_load_2d(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {   // ================= MMA issuer =================
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+    if (lane == 0 && crank == 0) {   // ================= MMA issuer (the leader CTA issues for a pair) =================
+      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint64_t desc_base = umma_desc_kmajor<SWB>(0u);      // everything except the start address
       int stage = 0, phase = 0, it = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-        const int as = it & 1, aphase = (it >> 1) & 1;
-        mbar_wait(tempty_bar + 8 * as, aphase ^ 1);
+      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+        const int as = it % NACC, aphase = (it / NACC) & 1;
+        mbar_wait(tempty_bar + 8 * as, aphase ^ 1);        // the epilogue (of both CTAs) has drained this buffer
         tc_fence_after();
         const uint32_t d_main = tmem_base + as * (2 * BN);
         const uint32_t d_corr = d_main + BN;
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sa = smem_base + stage * Cfg::STAGE;
-          const uint32_t sb = sa + 3 * Cfg::A_PLANE;
+          // descriptors: constant high word, low word = (smem address >> 4); planes / k-steps are plain adds
+          const uint64_t a0 = desc_base | (uint64_t)(((smem_base + stage * Cfg::STAGE) >> 4) & 0x3FFF);
+          const uint64_t b0 = a0 + (3 * Cfg::A_PLANE >> 4);
+          const uint32_t first = (kb == 0) ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
-            uint64_t ad[3], bd[3];
-#pragma unroll
-            for (int p = 0; p < 3; ++p) {
-              ad[p] = umma_desc_kmajor<SWB>(sa + p * Cfg::A_PLANE + ks * 32);
-              bd[p] = umma_desc_kmajor<SWB>(sb + p * Cfg::B_PLANE + ks * 32);
+            const uint64_t a1 = a0 + 2 * ks, a2 = a1 + (Cfg::A_PLANE >> 4), a3 = a2 + (Cfg::A_PLANE >> 4);
+            const uint64_t b1 = b0 + 2 * ks, b2 = b1 + (Cfg::B_PLANE >> 4), b3 = b2 + (Cfg::B_PLANE >> 4);
+            const uint32_t f = (ks == 0) ? first : 1u;
+            if constexpr (PAIR) {
+              tc_mma_bf16_2sm(d_corr, a2, b2, idesc, f);
+              tc_mma_bf16_2sm(d_corr, a1, b3, idesc, 1u);
+              tc_mma_bf16_2sm(d_corr, a3, b1, idesc, 1u);
+              tc_mma_bf16_2sm(d_corr, a1, b2, idesc, 1u);
+              tc_mma_bf16_2sm(d_corr, a2, b1, idesc, 1u);
+              tc_mma_bf16_2sm(d_main, a1, b1, idesc, f);
+            } else {
+              tc_mma_bf16(d_corr, a2, b2, idesc, f);      // x2 w2   (smallest terms first)
+              tc_mma_bf16(d_corr, a1, b3, idesc, 1u);     // x1 w3
+              tc_mma_bf16(d_corr, a3, b1, idesc, 1u);     // x3 w1
+              tc_mma_bf16(d_corr, a1, b2, idesc, 1u);     // x1 w2
+              tc_mma_bf16(d_corr, a2, b1, idesc, 1u);     // x2 w1
+              tc_mma_bf16(d_main, a1, b1, idesc, f);      // x1 w1
             }
-            const uint32_t first = (kb == 0 && ks == 0) ? 0u : 1u;
-            tc_mma_bf16(d_corr, ad[1], bd[1], idesc, first);
-            tc_mma_bf16(d_corr, ad[0], bd[2], idesc, 1u);
-            tc_mma_bf16(d_corr, ad[2], bd[0], idesc, 1u);
-            tc_mma_bf16(d_corr, ad[0], bd[1], idesc, 1u);
-            tc_mma_bf16(d_corr, ad[1], bd[0], idesc, 1u);
-            tc_mma_bf16(d_main, ad[0], bd[0], idesc, first);
           }
-          tc_commit(empty_bar + 8 * stage);
-          if (kb == num_k - 1) tc_commit(tfull_bar + 8 * as);
+          if constexpr (PAIR) {
+            tc_commit_2sm(empty_bar + 8 * stage);          // frees the stage in both CTAs
+            if (kb == num_k - 1) tc_commit_2sm(tfull_bar + 8 * as);
+          } else {
+            tc_commit(empty_bar + 8 * stage);
+            if (kb == num_k - 1) tc_commit(tfull_bar + 8 * as);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -159,19 +202,18 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
     const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
     int it = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+    for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
       const int nb = tile % num_n, r0 = tile / num_n;
       const int tb = r0 % num_t, b = r0 / num_t;
-      const int as = it & 1, aphase = (it >> 1) & 1;
-      mbar_wait(tfull_bar + 8 * as, aphase);
-      tc_fence_after();
+      const int as = it % NACC, aphase = (it / NACC) & 1;
+      bool waited = false;      // the accumulator wait is deferred until the first unit's global loads are in flight
       // Each unit = this warp's 32 rows x 16 columns.  The accumulators arrive row-per-lane (TMEM lane == row);
       // writing them out like that would make every global instruction touch 32 different lines, so the unit
       // is transposed through a padded shared buffer and ALL global traffic of the epilogue (y, residual,
       // accumulate, bf16 planes) is issued as 8 rows x 64 contiguous bytes per instruction.
       float* stg = epi_stage + ew * (32 * 20);
       const int chunk = lane & 3, rsub = lane >> 2;
-      const int t_base = tb * 128 + q * 32;
+      const int t_base = tb * BM + (int)crank * 128 + q * 32;
 #pragma unroll 1
       for (int u = half; u < BN / 16; u += 2) {
         const int n = nb * BN + u * 16 + chunk * 4;
@@ -187,6 +229,11 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
             if (g.res) rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
             if (g.accumulate) ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
           }
+        }
+        if (!waited) {
+          mbar_wait(tfull_bar + 8 * as, aphase);
+          tc_fence_after();
+          waited = true;
         }
         uint32_t r[16], rc[16];
         const uint32_t ta = tmem_base + as * (2 * BN) + u * 16 + ((uint32_t)(q * 32) << 16);
@@ -230,16 +277,27 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
         }
         __syncwarp();   // the staging buffer is reused by the next unit
       }
+      if (!waited) {
+        mbar_wait(tfull_bar + 8 * as, aphase);
+        tc_fence_after();
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar + 8 * as);
+      if (lane == 0) {
+        if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * as, 0));     // the leader's MMA issuer waits
+        else mbar_arrive(tempty_bar + 8 * as);
+      }
     }
   }
   tc_fence_before();
   __syncthreads();
+  if constexpr (PAIR) cluster_sync_all();      // no CTA exits (or frees TMEM) while its peer still reads its memory
   if (warp == 2) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    if constexpr (PAIR)
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -386,18 +444,34 @@ static int cmap_get(const void* p, uint64_t d0, uint64_t d1, uint64_t d2, uint32
   return 0;
 }
 
-template <int BN, int SWB>
+template <int BN, int SWB, int PAIR = 0>
 static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStream_t st) {
-  using Cfg = ConvTcCfg<BN, SWB>;
+  using Cfg = ConvTcCfg<BN, SWB, PAIR>;
   static bool attr = false;
   if (!attr) {
-    cudaError_t e = cudaFuncSetAttribute(conv_bf16x3_kernel<BN, SWB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+    cudaError_t e =
+        cudaFuncSetAttribute(conv_bf16x3_kernel<BN, SWB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "conv_tc", (long long)e);
     attr = true;
   }
-  const int64_t tiles = (int64_t)a.B * cdiv64(a.T, 128) * cdiv64(a.Cout, BN);
-  const int grid = (int)(tiles < g_ctc_sms ? tiles : g_ctc_sms);
-  conv_bf16x3_kernel<BN, SWB><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
+  const int64_t tiles = (int64_t)a.B * cdiv64(a.T, PAIR ? 256 : 128) * cdiv64(a.Cout, BN);
+  if (PAIR) {
+    const int64_t pairs = tiles < g_ctc_sms / 2 ? tiles : g_ctc_sms / 2;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(2 * pairs));
+    cfg.blockDim = dim3(384);
+    cfg.dynamicSmemBytes = Cfg::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<BN, SWB, PAIR>, maps, a);
+    if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cluster launch failed: %lld", "conv_tc", (long long)e);
+  } else {
+    const int grid = (int)(tiles < g_ctc_sms ? tiles : g_ctc_sms);
+    conv_bf16x3_kernel<BN, SWB, PAIR><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
+  }
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -441,7 +515,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
                                                                           plane_stride, total4);
     MTTS_CHECK_LAUNCH();
   }
-  const int SWB = p.Cin >= 64 ? 128 : 64;
+  int SWB = p.Cin >= 64 ? 128 : 64;
   // N-tile width: the widest tile that still gives every SM a tile; under-filled grids are latency-bound
   // (one 128x128xK tile per CTA is paced by TMA round trips, not by the tensor pipe), so narrow tiles win there
   int BN = 32;
@@ -454,11 +528,28 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
       if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(g_ctc_sms * 4) / 5) break;
     }
   }
+  // CTA pairs (cta_group::2): two SMs share one 256 x 128 tile; each stages its own 128 activation rows and HALF of the
+  // weight tile, so a quarter fewer bytes cross L2 -> SM and a quarter fewer operand bytes are read from shared memory
+  // per FLOP.  Measured (tools/bench_tc_shapes.py): +1..3 % on the dense layers, -5 % on the ragged-T convolutions
+  // (256-row tiles waste more of the last tile), so pairs are used for k = 1 only.
+  // Tuning switches (diagnostics): MEGATTS2_TC_PAIR = 0 | 1 | 2 (2: 32-wide K-slabs), MEGATTS2_TC_SWB64 = 1.
+  const char* pe = getenv("MEGATTS2_TC_PAIR");
+  const int pair_mode = pe ? atoi(pe) : 1;
+  const char* se = getenv("MEGATTS2_TC_SWB64");
+  if (se && se[0] == '1') SWB = 64;
+  bool pair = false;
+  if (pair_mode && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || pair_mode >= 3)) {
+    const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
+    const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
+    pair = t256 >= (int64_t)(g_ctc_sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
+    if (pair && (pair_mode == 2 || pair_mode == 4)) SWB = 64;      // 32-wide K-slabs: 5 stages of 36 KB instead of 2 of 72 KB
+  }
+  const int b_rows = pair ? BN / 2 : BN;
   ConvTcMaps maps;
   for (int q = 0; q < 3; ++q) {
     MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2, 128, SWB, &maps.a[q]));
     MTTS_TRY(cmap_get((const __nv_bfloat16*)p.w_tc + (int64_t)q * p.k * p.Cout * p.Cin, (uint64_t)p.Cin,
-                      (uint64_t)p.k * p.Cout, 0, SWB / 2, BN, SWB, &maps.b[q]));
+                      (uint64_t)p.k * p.Cout, 0, SWB / 2, b_rows, SWB, &maps.b[q]));
   }
   ConvTcArgs a;
   a.B = p.B; a.T = p.Tout; a.Cin = p.Cin; a.Cout = p.Cout; a.k = p.k; a.dil = p.dil;
@@ -468,6 +559,9 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.out_shift = p.out_shift; a.ybe = p.y_batch_elems ? p.y_batch_elems : (int64_t)p.Tout * p.ldy;
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
+  if (pair) return SWB == 128 ? conv_tc_launch<128, 128, 1>(maps, a, st) : conv_tc_launch<128, 64, 1>(maps, a, st);
+  if (SWB == 64 && BN == 128) return conv_tc_launch<128, 64>(maps, a, st);
+  if (SWB == 64 && BN == 64) return conv_tc_launch<64, 64>(maps, a, st);
   if (SWB == 64) return conv_tc_launch<32, 64>(maps, a, st);
   if (BN == 128) return conv_tc_launch<128, 128>(maps, a, st);
   if (BN == 64) return conv_tc_launch<64, 128>(maps, a, st);

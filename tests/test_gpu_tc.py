@@ -26,6 +26,9 @@ CASES = [
     dict(M=300, K=768, N=2304, bias=True),                         # ADM qkv
     dict(M=640, K=72, N=192),                                      # K tail, N not a multiple of 128
     dict(M=129, K=1024, N=1024, res=True),
+    dict(M=8192, K=4096, N=1024, bias=True, res=True),             # 256-wide tiles, long K
+    dict(M=5000, K=1024, N=768, bias=True, relu=True),             # 256-wide tiles, M tail
+    dict(M=16384, K=80, N=512, bias=True),                         # 256-wide tiles, K tail inside a 32-wide slab
 ]
 
 
@@ -102,6 +105,17 @@ CONV_TC_CASES = [
     dict(B=2, T=64, Cin=512, Cout=1024, k=5, post=1),                                  # conv-FF first conv
     dict(B=2, T=64, Cin=1024, Cout=512, k=5, res=True),                                # conv-FF second conv
     dict(B=1, T=130, Cin=96, Cout=160, k=3, pad_mode=2),                               # odd sizes: K and N tails
+    # full-machine grids (>= 148 tiles), long sequences
+    dict(B=4, T=5000, Cin=64, Cout=64, k=7, dil=3, pad_mode=1, pre=2, res=True),
+    dict(B=4, T=5000, Cin=64, Cout=64, k=11, dil=5, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),
+    dict(B=4, T=5000, Cin=64, Cout=64, k=3, dil=1, pad_mode=1, pre=2),
+    dict(B=4, T=5001, Cin=32, Cout=32, k=11, dil=5, pad_mode=1, pre=2, res=True),
+    dict(B=4, T=5000, Cin=32, Cout=32, k=3, dil=1, pad_mode=1, pre=2),
+    dict(B=4, T=4999, Cin=32, Cout=32, k=7, dil=3, pad_mode=0),
+    # 256-wide tiles (Cout >= 256 and enough tiles to fill the machine)
+    dict(B=8, T=2000, Cin=256, Cout=256, k=7, dil=3, pad_mode=1, pre=2, res=True, acc=True, scale=1 / 3),
+    dict(B=8, T=1001, Cin=512, Cout=512, k=3, pre=1, post=1),
+    dict(B=16, T=700, Cin=192, Cout=768, k=5, pad_mode=2),
 ]
 
 
@@ -167,6 +181,18 @@ def test_conv_stacks_tc_vs_oracle(weights_cpu):
     x = torch.randn(2, 768, 140, generator=gen(64))
     dec_ref = R.convnet(R.SD(weights_cpu("g"), "decoder."), x, 5, 4, 2)
     assert (G.decoder(x.to(DEV)).cpu() - dec_ref).abs().max().item() < 5e-4
+
+
+def test_hifigan_full_grid_vs_oracle(weights_cpu):
+    """B*L large enough that every stage launches full-machine grids inside the fused ResBlock flow."""
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    hifi = helpers.build_hifigan(weights_cpu("hifigan"), DEV)
+    mel = torch.randn(4, 80, 64, generator=gen(66)) * 2 - 4
+    ref = R.hifigan_generator(weights_cpu("hifigan"), mel, W.HIFIGAN_CFG)
+    hifi.generator.engine = 1
+    w1 = hifi.decode_batch(mel.to(DEV))
+    assert (w1.cpu() - ref).abs().max().item() < 1e-4
 
 
 def test_hifigan_tc_vs_oracle(weights_cpu):
