@@ -267,15 +267,20 @@ def run_b200(args):
                     "achieved_tflops": round(fl_ / (ms_ / 1e3) / 1e12, 2) if ms_ > 0 else 0.0,
                     "share_of_step": round(ms_ / step_ms, 3)}
         classes = {"fp32_ffma_tapconv_kernel": cls(sp[0], sp[1], sp[2]),
-                   "tcgen05_bf16x3_gemm_and_conv_kernels (incl. their split kernels)": cls(sp[3], sp[4], sp[5])}
+                   "tcgen05_bf16x3_tap_gemm_kernels (incl. their activation-split kernels)": cls(sp[3], sp[4], sp[5])}
         dom_tc = sp[3] >= sp[0]
         d_ms, d_fl = (sp[3], sp[4]) if dom_tc else (sp[0], sp[1])
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
         roofline = {"bound": "tensor",
-                    "kernel": ("gemm_bf16x3_kernel / conv_bf16x3_kernel (tcgen05 tap-GEMM, 6 bf16 MMAs per fp32-grade product)"
+                    "kernel": ("conv_bf16x3_kernel (tcgen05 tap-GEMM: every Linear / Conv1d / ConvTranspose1d; 6 bf16 MMAs per "
+                               "fp32-grade product; single-CTA and cta_group::2 pair variants)"
                                if dom_tc else "tapconv_kernel (fp32 FFMA tap-GEMM)"),
                     "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
                     "traffic": None,
+                    "traffic_note": "achieved aggregates ~4.9k launches of many shapes, so there is no single per-launch DRAM "
+                                    "figure; for the representative launch (PLM FF1 GEMM, M 5888, K 1024, N 4096) ncu --set full "
+                                    "measured 61.4 MB read + 62.3 MB written against 158 MB algorithmic (operands and result "
+                                    "stay L2-resident): profiles/r1_tc_engine_bounds.md",
                     "peak_source": f"{pk_src} dense bf16 (sustained). achieved = algorithmic fp32-grade FLOPs (2*M*N*K) / CUDA-event "
                                    "time of the launches; the bf16x3 scheme issues 6 bf16 MMAs per such FLOP pair, so its "
                                    "ceiling is peak/6",

@@ -182,8 +182,9 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
   constexpr int BQ = RW * NW, BKV = 32, NT = NW * 32;
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                        // [BQ][DH]
-  float* Ks = Qs + BQ * DH;              // [BKV][DH+1]
-  float* Vs = Ks + BKV * (DH + 1);       // [BKV][DH]
+  constexpr int KS = DH + 4;             // K row stride: 16-byte aligned rows, conflict-free 128-bit reads (lane stride 4 banks)
+  float* Ks = Qs + BQ * DH;              // [BKV][KS]
+  float* Vs = Ks + BKV * KS;             // [BKV][DH]
   float* Ps = Vs + BKV * DH;             // [NW][RW][32]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
@@ -230,15 +231,14 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
           kv = *reinterpret_cast<const float4*>(kb + (int64_t)(k0 + r) * p.k_st + d);
           vv = *reinterpret_cast<const float4*>(vb + (int64_t)(k0 + r) * p.v_st + d);
         }
-        float* kd = Ks + r * (DH + 1) + d;
-        kd[0] = kv.x; kd[1] = kv.y; kd[2] = kv.z; kd[3] = kv.w;
+        *reinterpret_cast<float4*>(Ks + r * KS + d) = kv;
         *reinterpret_cast<float4*>(Vs + r * DH + d) = vv;
       }
     } else {
       for (int i = tid; i < BKV * DH; i += NT) {
         const int r = i / DH, d = i - r * DH;
         const bool ok = k0 + r < p.Tk;
-        Ks[r * (DH + 1) + d] = ok ? kb[(int64_t)(k0 + r) * p.k_st + d] : 0.f;
+        Ks[r * KS + d] = ok ? kb[(int64_t)(k0 + r) * p.k_st + d] : 0.f;
         Vs[r * DH + d] = ok ? vb[(int64_t)(k0 + r) * p.v_st + d] : 0.f;
       }
     }
@@ -247,13 +247,21 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
     float s[RW];
 #pragma unroll
     for (int i = 0; i < RW; ++i) s[i] = 0.f;
-    const float* kr = Ks + lane * (DH + 1);
+    // 128-bit shared loads: one K chunk per lane + RW broadcast Q chunks feed 4 * RW FMAs (the scalar form issued
+    // 9 loads per 8 FMAs and was load-issue bound); the d order of every dot product is unchanged
+    const float* kr = Ks + lane * KS;
     const float* qr = Qs + (w * RW) * DH;
-#pragma unroll 8
-    for (int d = 0; d < DH; ++d) {
-      const float kv = kr[d];
+#pragma unroll 4
+    for (int d = 0; d < DH; d += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(kr + d);
 #pragma unroll
-      for (int i = 0; i < RW; ++i) s[i] = fmaf(qr[i * DH + d], kv, s[i]);
+      for (int i = 0; i < RW; ++i) {
+        const float4 qv = *reinterpret_cast<const float4*>(qr + i * DH + d);
+        s[i] = fmaf(qv.x, kv.x, s[i]);
+        s[i] = fmaf(qv.y, kv.y, s[i]);
+        s[i] = fmaf(qv.z, kv.z, s[i]);
+        s[i] = fmaf(qv.w, kv.w, s[i]);
+      }
     }
     const bool kvalid = (k0 + lane) < p.Tk;
 #pragma unroll
@@ -273,16 +281,22 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
     }
     __syncwarp();
     const float* pw = Ps + (w * RW) * 32;
-#pragma unroll 4
-    for (int j = 0; j < BKV; ++j) {
-      float pj[RW];
+#pragma unroll 2
+    for (int j = 0; j < BKV; j += 4) {
+      float4 pj[RW];
 #pragma unroll
-      for (int i = 0; i < RW; ++i) pj[i] = pw[i * 32 + j];
+      for (int i = 0; i < RW; ++i) pj[i] = *reinterpret_cast<const float4*>(pw + i * 32 + j);
 #pragma unroll
       for (int ii = 0; ii < NI; ++ii) {
-        const float vv = Vs[j * DH + lane + 32 * ii];
+        const float v0 = Vs[(j + 0) * DH + lane + 32 * ii], v1 = Vs[(j + 1) * DH + lane + 32 * ii];
+        const float v2 = Vs[(j + 2) * DH + lane + 32 * ii], v3 = Vs[(j + 3) * DH + lane + 32 * ii];
 #pragma unroll
-        for (int i = 0; i < RW; ++i) acc[i][ii] = fmaf(pj[i], vv, acc[i][ii]);
+        for (int i = 0; i < RW; ++i) {
+          acc[i][ii] = fmaf(pj[i].x, v0, acc[i][ii]);
+          acc[i][ii] = fmaf(pj[i].y, v1, acc[i][ii]);
+          acc[i][ii] = fmaf(pj[i].z, v2, acc[i][ii]);
+          acc[i][ii] = fmaf(pj[i].w, v3, acc[i][ii]);
+        }
       }
     }
     __syncwarp();
@@ -326,7 +340,7 @@ template <int NI, int RW, int NW>
 static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   constexpr int DH = 32 * NI;
   constexpr int BQ = RW * NW;
-  const size_t smem = sizeof(float) * (BQ * DH + 32 * (DH + 1) + 32 * DH + NW * RW * 32);
+  const size_t smem = sizeof(float) * (BQ * DH + 32 * (DH + 4) + 32 * DH + NW * RW * 32);
   static bool configured = false;   // per-process, per-instantiation; attribute set is idempotent
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI, RW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
