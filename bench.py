@@ -302,6 +302,7 @@ def run_b200(args):
                     "h2d_bytes_per_step": world * (wav_h.numel() * 4 + phone_h.numel() * 8),
                     "d2h_bytes_per_step": world * out_h.numel() * 4},
             "gpu_launches": int(launches),
+            "hbm_peak_bytes": int(torch.cuda.max_memory_allocated(dev)),
             "clocks": clocks,
             "roofline": roofline,
             "cpu_baseline": cpu,

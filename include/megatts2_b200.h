@@ -246,6 +246,19 @@ int mtts_adm_infer_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb,
                        int32_t B, int32_t T, int32_t* dur_out, float* raw_out,
                        void* workspace, int64_t workspace_bytes, void* stream);
 
+/* Opt-in causal KV-cache decode (NOT what the reference's infer() computes).  Follows the TRAINING
+ * semantics of MegaPLM.forward / MegaADM.forward (causal=True, models/megatts2.py:158, 244): row t attends to rows <= t,
+ * so a step computes one row per utterance and appends its K/V to per-layer caches - O(T) instead of the O(T^2) full
+ * recompute.  Same arguments and outputs as the *_infer_f32 entry points; linear feed-forward encoders only. */
+int64_t mtts_plm_decode_causal_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T);
+int mtts_plm_decode_causal_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld,
+                               int32_t B, int32_t T, int64_t* codes_out, float* logits_out,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+int64_t mtts_adm_decode_causal_workspace_bytes(const mtts_adm* m, int32_t B, int32_t T);
+int mtts_adm_decode_causal_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld,
+                               int32_t B, int32_t T, int32_t* dur_out, float* raw_out,
+                               void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ConvNet family (modules/convnet.py).  One ConvBlock = ReLU -> Conv1d(C,C,k,same) -> LN(C). */
 typedef struct { const float *w, *b, *ln_g, *ln_b; const void* w_tc; } mtts_conv_block;   /* w packed (k,C,C); w_tc (3,k,C,C) bf16 or NULL */
 

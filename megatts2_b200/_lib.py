@@ -128,6 +128,10 @@ SIGNATURES = {
     "mtts_plm_infer_f32": (C.c_int, [C.POINTER(PLM), vp, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
     "mtts_adm_infer_workspace_bytes": (i64, [C.POINTER(ADM), i32, i32]),
     "mtts_adm_infer_f32": (C.c_int, [C.POINTER(ADM), vp, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
+    "mtts_plm_decode_causal_workspace_bytes": (i64, [C.POINTER(PLM), i32, i32]),
+    "mtts_plm_decode_causal_f32": (C.c_int, [C.POINTER(PLM), vp, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
+    "mtts_adm_decode_causal_workspace_bytes": (i64, [C.POINTER(ADM), i32, i32]),
+    "mtts_adm_decode_causal_f32": (C.c_int, [C.POINTER(ADM), vp, i64, i32, i32, i32, vp, vp, vp, i64, vp]),
     "mtts_convnet_workspace_bytes": (i64, [C.POINTER(ConvNet), i32, i32]),
     "mtts_convnet_forward_f32": (C.c_int, [C.POINTER(ConvNet), vp, i64, i32, vp, i64, i32, i32, i32, vp, i64, vp]),
     "mtts_convnet_double_out_len": (i32, [C.POINTER(ConvNetDouble), i32]),

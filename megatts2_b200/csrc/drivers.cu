@@ -317,6 +317,147 @@ static int adm_infer(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_l
 }
 
 // ------------------------------------------------------------------------------------------
+// Opt-in causal KV-cache decode.  NOT the parity path of infer(): the reference's infer()
+// re-runs the stack bidirectionally every step (megatts2.py:177, 271).  This decode follows the TRAINING
+// semantics instead (causal=True, megatts2.py:158, 244): row t attends to rows <= t only, so rows < t never change
+// and step t computes one row per utterance, appending its K/V to per-layer caches.  Its oracle is the
+// teacher-forced causal forward (MegaPLM.forward / MegaADM.forward) evaluated on the decode's own prefix.
+struct CausalBufs {
+  float *x, *h, *qkv, *a, *f, *kv;     // (B,D) (B,D) (B,3D) (B,D) (B,F); kv: n_layers x (B, T, 2D) [k | v]
+  char* scratch; int64_t scratch_bytes;
+};
+
+static int64_t causal_ws_floats(const mtts_encoder* e, int B, int T) {
+  const int64_t D = e->d_model, F = e->ff_dim;
+  const int64_t wide = 3 * D > F ? 3 * D : F;
+  return (int64_t)B * (D + D + 3 * D + D + F) + (int64_t)e->n_layers * B * T * 2 * D + 16 * (int64_t)B * wide + 2048 + 8 * 64;
+}
+
+static int causal_take(const mtts_encoder* e, int B, int T, Arena& ar, CausalBufs& cb) {
+  const int64_t D = e->d_model, F = e->ff_dim;
+  const int64_t wide = 3 * D > F ? 3 * D : F;
+  cb.x = ar.take<float>((int64_t)B * D);
+  cb.h = ar.take<float>((int64_t)B * D);
+  cb.qkv = ar.take<float>((int64_t)B * 3 * D);
+  cb.a = ar.take<float>((int64_t)B * D);
+  cb.f = ar.take<float>((int64_t)B * F);
+  cb.kv = ar.take<float>((int64_t)e->n_layers * B * T * 2 * D);
+  cb.scratch_bytes = 16 * (int64_t)B * wide * 4 + 4096;
+  cb.scratch = ar.take<char>(cb.scratch_bytes);
+  return ar.ok() ? 0 : fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "causal decode", ar.off);
+}
+
+// one decode step: cb.x holds row t of the input (B,D) on entry and the stack's output row on return
+static int causal_step(const mtts_encoder* e, int B, int T, int t, const CausalBufs& cb, cudaStream_t st) {
+  const int D = e->d_model, H = e->n_heads, F = e->ff_dim, dh = D / H;
+  const float scale = 1.0f / sqrtf((float)dh);
+  auto skinny = [&](mtts_conv_params& q) { q.tc_scratch = cb.scratch; q.tc_scratch_bytes = cb.scratch_bytes; };   // split-K room
+  for (int l = 0; l < e->n_layers; ++l) {
+    const mtts_encoder_layer& L = e->layers[l];
+    float* kv = cb.kv + (int64_t)l * B * T * 2 * D;
+    MTTS_TRY(layernorm(cb.x, D, L.ln1_g, L.ln1_b, nullptr, 0, cb.h, D, B, D, 1e-5f, 0, 0, st));
+    mtts_conv_params pq = linear_params(cb.h, D, L.w_qkv, L.b_qkv, cb.qkv, 3 * D, B, D, 3 * D);
+    skinny(pq);
+    MTTS_TRY(conv1d(pq, st));
+    // append this row's [k | v] to the cache at position t
+    MTTS_TRY(copy_strided(cb.qkv + D, 3 * D, 3 * D, 1, kv + (int64_t)t * 2 * D, (int64_t)T * 2 * D, 2 * D, 1, B, 1, 2 * D, 0, st));
+    mtts_attn_params ap;
+    memset(&ap, 0, sizeof(ap));
+    ap.B = B; ap.H = H; ap.Tq = 1; ap.Tk = t + 1; ap.dh = dh; ap.scale = scale;
+    ap.q = cb.qkv; ap.q_sb = 3 * D; ap.q_st = 3 * D;
+    ap.k = kv; ap.k_sb = (int64_t)T * 2 * D; ap.k_st = 2 * D;
+    ap.v = kv + D; ap.v_sb = (int64_t)T * 2 * D; ap.v_st = 2 * D;
+    ap.o = cb.a; ap.o_sb = D; ap.o_st = D;
+    MTTS_TRY(attention(ap, st));
+    mtts_conv_params po = linear_params(cb.a, D, L.w_o, L.b_o, cb.x, D, B, D, D);
+    po.res = cb.x; po.ldr = D;
+    skinny(po);
+    MTTS_TRY(conv1d(po, st));
+    MTTS_TRY(layernorm(cb.x, D, L.ln2_g, L.ln2_b, nullptr, 0, cb.h, D, B, D, 1e-5f, 0, 0, st));
+    mtts_conv_params p1 = linear_params(cb.h, D, L.w_ff1, L.b_ff1, cb.f, F, B, D, F);
+    p1.post_act = MTTS_ACT_RELU;
+    skinny(p1);
+    MTTS_TRY(conv1d(p1, st));
+    mtts_conv_params p2 = linear_params(cb.f, F, L.w_ff2, L.b_ff2, cb.x, D, B, F, D);
+    p2.res = cb.x; p2.ldr = D;
+    skinny(p2);
+    MTTS_TRY(conv1d(p2, st));
+  }
+  return 0;
+}
+
+static int64_t plm_causal_ws_floats(const mtts_plm* m, int B, int T) {
+  return causal_ws_floats(&m->enc, B, T) + (int64_t)B * m->vq_bins + 2 * ((int64_t)B * (T + 1) + 64) + 4 * 64;
+}
+
+static int plm_decode_causal(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_ld, int B, int T, int64_t* codes_out,
+                             float* logits_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int D = m->enc.d_model, V = m->vq_bins;
+  MTTS_REQUIRE(D == m->tc_dim + m->vq_dim, "d_model != tc_dim + vq_dim");
+  MTTS_REQUIRE(tc && codes_out && m->pc_embedding && m->w_predict && m->pe, "null pointer");
+  MTTS_REQUIRE(!m->enc.conv_ff && D % m->enc.n_heads == 0, "needs a linear feed-forward encoder");
+  if (B <= 0 || T <= 0) return 0;
+  Arena ar(ws, ws_bytes);
+  float* logits = ar.take<float>((int64_t)B * V);
+  int64_t* codes = ar.take<int64_t>((int64_t)B * (T + 1));
+  CausalBufs cb;
+  MTTS_TRY(causal_take(&m->enc, B, T, ar, cb));
+  MTTS_TRY(fill_i64(codes, T + 1, B, (int64_t)V, st));   // BOS = vq_bins (megatts2.py:170-171)
+  for (int t = 0; t < T; ++t) {
+    // row t of the input: cat(tc[:, t], emb[codes[:, t]]) + alpha * pe[t]   (megatts2.py:154-157)
+    MTTS_TRY(plm_build_input(tc + (int64_t)t * tc_ld, tc_sb, tc_ld, m->tc_dim, codes + t, T + 1, m->pc_embedding, m->vq_dim,
+                             V + 2, m->pe + (int64_t)t * D, m->pe_alpha, B, 1, cb.x, st));
+    MTTS_TRY(causal_step(&m->enc, B, T, t, cb, st));
+    float* lg = logits_out ? logits_out + (int64_t)t * V : logits;
+    const int64_t lg_sb = logits_out ? (int64_t)T * V : V;
+    mtts_conv_params p = linear_params(cb.x, D, m->w_predict, nullptr, lg, V, B, D, V);
+    p.y_batch_stride = lg_sb;
+    p.B = B; p.Tin = 1; p.Tout = 1; p.x_batch_stride = D;
+    p.tc_scratch = cb.scratch; p.tc_scratch_bytes = cb.scratch_bytes;
+    MTTS_TRY(conv1d(p, st));
+    MTTS_TRY(argmax_rows(lg, lg_sb, V, B, codes + (t + 1), T + 1, codes_out + t, T, st));
+  }
+  return 0;
+}
+
+static int64_t adm_causal_ws_floats(const mtts_adm* m, int B, int T) {
+  return causal_ws_floats(&m->enc, B, T) + (int64_t)B * T * m->tc_emb_dim + (int64_t)B * (T + 1) + 4 * 64;
+}
+
+static int adm_decode_causal(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_ld, int B, int T, int32_t* dur_out,
+                             float* raw_out, void* ws, int64_t ws_bytes, cudaStream_t st) {
+  const int D = m->enc.d_model;
+  MTTS_REQUIRE(D == m->emb_dim + m->tc_emb_dim, "d_model != emb_dim + tc_emb_dim");
+  MTTS_REQUIRE(tc && dur_out && m->w_dt && m->w_tc && m->w_predict && m->pe, "null pointer");
+  MTTS_REQUIRE(!m->enc.conv_ff && D % m->enc.n_heads == 0, "needs a linear feed-forward encoder");
+  if (B <= 0 || T <= 0) return 0;
+  Arena ar(ws, ws_bytes);
+  float* tc_emb = ar.take<float>((int64_t)B * T * m->tc_emb_dim);
+  float* praw = ar.take<float>((int64_t)B * (T + 1));
+  CausalBufs cb;
+  MTTS_TRY(causal_take(&m->enc, B, T, ar, cb));
+  {
+    mtts_conv_params p;
+    memset(&p, 0, sizeof(p));
+    p.x = tc; p.ldx = tc_ld; p.x_batch_stride = tc_sb;
+    p.w = m->w_tc;
+    p.y = tc_emb; p.ldy = m->tc_emb_dim; p.y_batch_stride = (int64_t)T * m->tc_emb_dim;
+    p.B = B; p.Tin = T; p.Tout = T; p.Cin = m->tc_dim; p.Cout = m->tc_emb_dim; p.k = 1; p.stride = 1; p.dil = 1;
+    p.out_scale = 1.0f;
+    MTTS_TRY(conv1d(p, st));
+  }
+  MTTS_TRY(fill_f32(praw, T + 1, B, 0.0f, st));   // p_code = [[0]] (megatts2.py:262-263)
+  for (int t = 0; t < T; ++t) {
+    MTTS_TRY(adm_build_input(tc_emb + (int64_t)t * m->tc_emb_dim, (int64_t)T * m->tc_emb_dim, m->tc_emb_dim, m->tc_emb_dim,
+                             praw + t, T + 1, m->w_dt, m->emb_dim, m->pe + (int64_t)t * D, m->pe_alpha, B, 1, cb.x, st));
+    MTTS_TRY(causal_step(&m->enc, B, T, t, cb, st));
+    MTTS_TRY(adm_readout(cb.x, D, m->w_predict, B, praw, T + 1, t + 1, st));
+  }
+  MTTS_TRY(adm_finalize(praw, T + 1, B, T, dur_out, raw_out, st));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // ConvNet family (modules/convnet.py), channels-last
 struct StackBufs { float *tmp, *h1; };
 
@@ -667,6 +808,25 @@ int mtts_adm_infer_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb,
                        int32_t* dur_out, float* raw_out, void* workspace, int64_t workspace_bytes, void* stream) {
   MTTS_REQUIRE(m && m->enc.layers && workspace, "null pointer");
   return adm_infer(m, tc_latent, tc_sb, tc_ld, B, T, dur_out, raw_out, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int64_t mtts_plm_decode_causal_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) {
+  return plm_causal_ws_floats(m, B, T) * 4 + 8192;
+}
+int mtts_plm_decode_causal_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,
+                               int64_t* codes_out, float* logits_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(m && m->enc.layers && workspace, "null pointer");
+  return plm_decode_causal(m, tc_latent, tc_sb, tc_ld, B, T, codes_out, logits_out, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
+}
+int64_t mtts_adm_decode_causal_workspace_bytes(const mtts_adm* m, int32_t B, int32_t T) {
+  return adm_causal_ws_floats(m, B, T) * 4 + 8192;
+}
+int mtts_adm_decode_causal_f32(const mtts_adm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,
+                               int32_t* dur_out, float* raw_out, void* workspace, int64_t workspace_bytes, void* stream) {
+  MTTS_REQUIRE(m && m->enc.layers && workspace, "null pointer");
+  return adm_decode_causal(m, tc_latent, tc_sb, tc_ld, B, T, dur_out, raw_out, workspace, workspace_bytes,
+                           (cudaStream_t)stream);
 }
 
 int64_t mtts_convnet_workspace_bytes(const mtts_convnet* n, int32_t B, int32_t T) { return convnet_ws_floats(n, B, T) * 4 + 4096; }

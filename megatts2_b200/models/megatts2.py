@@ -150,6 +150,28 @@ class MegaPLM(pack.PlanMixin, nn.Module):
                                        ws.data_ptr(), ws.numel(), ops._stream()))
         return (codes, logits) if return_logits else codes
 
+    def infer_causal(self, tc_latent: torch.Tensor, return_logits: bool = False):
+        """OPT-IN causal KV-cache greedy decode - NOT what the reference's ``infer`` computes.
+
+        ``infer`` re-runs the stack bidirectionally every step (models/megatts2.py:177); this decode follows the
+        *training* semantics of ``forward`` (causal=True, models/megatts2.py:158): row t attends to rows <= t, so
+        each step computes one row per utterance against per-layer K/V caches (O(T) instead of O(T^2)).  Its
+        logits equal the teacher-forced ``forward`` logits evaluated on its own output.  Same I/O as ``infer``."""
+        _eval_only(self)
+        tc = ops._dev(tc_latent, name="tc_latent")
+        if tc.stride(2) != 1:
+            tc = tc.contiguous()
+        B, T, _ = tc.shape
+        pl = self._plan_get(tc.device, T)
+        lib = L.lib()
+        codes = torch.empty(B, T, dtype=torch.int64, device=tc.device)
+        logits = torch.empty(B, T, self.vq_bins, dtype=torch.float32, device=tc.device) if return_logits else None
+        ws = ops.workspace(lib.mtts_plm_decode_causal_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
+        L.check(lib.mtts_plm_decode_causal_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
+                                               codes.data_ptr(), logits.data_ptr() if return_logits else None,
+                                               ws.data_ptr(), ws.numel(), ops._stream()))
+        return (codes, logits) if return_logits else codes
+
     @classmethod
     def from_pretrained(cls, ckpt: str, config: str) -> "MegaPLM":
         with open(config, "r") as f:
@@ -227,6 +249,26 @@ class MegaADM(pack.PlanMixin, nn.Module):
         L.check(lib.mtts_adm_infer_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
                                        dur.data_ptr(), raw.data_ptr() if return_raw else None,
                                        ws.data_ptr(), ws.numel(), ops._stream()))
+        dur = dur.unsqueeze(-1)
+        return (dur, raw) if return_raw else dur
+
+    def infer_causal(self, tc_latents: torch.Tensor, return_raw: bool = False):
+        """OPT-IN causal KV-cache duration decode - NOT what the reference's ``infer`` computes:
+        the training semantics of ``forward`` (causal=True, models/megatts2.py:244) with ``infer``'s raw-float
+        feedback and final rounding; one row per utterance per step against K/V caches.  Same I/O as ``infer``."""
+        _eval_only(self)
+        tc = ops._dev(tc_latents, name="tc_latents")
+        if tc.stride(2) != 1:
+            tc = tc.contiguous()
+        B, T, _ = tc.shape
+        pl = self._plan_get(tc.device, T)
+        lib = L.lib()
+        dur = torch.empty(B, T, dtype=torch.int32, device=tc.device)
+        raw = torch.empty(B, T, dtype=torch.float32, device=tc.device) if return_raw else None
+        ws = ops.workspace(lib.mtts_adm_decode_causal_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
+        L.check(lib.mtts_adm_decode_causal_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
+                                               dur.data_ptr(), raw.data_ptr() if return_raw else None,
+                                               ws.data_ptr(), ws.numel(), ops._stream()))
         dur = dur.unsqueeze(-1)
         return (dur, raw) if return_raw else dur
 
@@ -391,16 +433,19 @@ class Megatts(nn.Module):
 
     @torch.no_grad()
     def synthesize(self, phone_tokens: torch.Tensor, mels: torch.Tensor, forced_durations: torch.Tensor = None,
-                   return_intermediates: bool = False):
+                   return_intermediates: bool = False, causal_decode: bool = False):
         """phone_tokens (B,Tp) int64, mels (B,Tm,80) prompt mel (frames-major) -> wav (B,1,256*(sum d + 10)).
         Steps = models/megatts2.py:354-370.  ``forced_durations`` (B,Tp) int32 replaces the ADM output
-        for shape control (the ADM still runs)."""
+        for shape control (the ADM still runs).  ``causal_decode=True`` swaps both AR loops for the opt-in causal
+        KV-cache decode (training semantics; NOT the reference's infer() - different ids)."""
         tc_latent = self.generator.mrte.tc_latent(phone_tokens, mels)
-        dt = self.adm.infer(tc_latent)[..., 0]
+        adm_decode = self.adm.infer_causal if causal_decode else self.adm.infer
+        plm_decode = self.plm.infer_causal if causal_decode else self.plm.infer
+        dt = adm_decode(tc_latent)[..., 0]
         d_used = dt if forced_durations is None else forced_durations.to(dt.device, torch.int32)
         tc_expand = self.lr(tc_latent, d_used)                    # one host sync for the output length
         tc8 = ops.maxpool_time(tc_expand, 8)
-        p_codes = self.plm.infer(tc8)
+        p_codes = plm_decode(tc8)
         mel = self.generator.decode_mel_cl(tc_expand, p_codes)    # (B, L, 80) channels-last
         wav = self.hifi_gan.decode_batch_cl(mel)
         if return_intermediates:

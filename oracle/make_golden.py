@@ -208,6 +208,38 @@ def main():
         close("plm forward", o_f, f_ref, 2e-3)
         save("plm", tc8=tc8, ids=ids_ref, logits=lg_ref, fwd_logits=f_ref)
 
+        # ---- 8f-1 (next row): opt-in causal decode, pinned on the reference's TRAINING forward (causal=True)
+        print("causal decode (greedy / raw-feedback loops over the reference's teacher-forced forward)")
+        codes = torch.full((2, 1), 1024, dtype=torch.int64)
+        c_lgs = []
+        for t in range(12):
+            pc = torch.cat([codes, codes[:, :1]], 1)
+            lg = plm(tc8[:, :t + 1], pc, torch.full((2,), t + 1, dtype=torch.int32))[0][:, -1]
+            c_lgs.append(lg)
+            codes = torch.cat([codes, lg.argmax(-1, keepdim=True)], 1)
+        c_ids, c_lg = codes[:, 1:], torch.stack(c_lgs, 1)
+        o_cids, o_clg = R.plm_infer_causal(R.SD(psd), tc8, pcfg, return_logits=True)
+        assert torch.equal(o_cids, c_ids), (o_cids, c_ids)
+        close("plm causal logits", o_clg, c_lg, 2e-3)
+        # self-consistency: one teacher-forced pass over the decode's own output reproduces every step
+        f_all, _ = plm(tc8, torch.cat([torch.full((2, 1), 1024), c_ids], 1), torch.tensor([12, 12], dtype=torch.int32))
+        close("plm causal == teacher-forced", f_all, c_lg, 2e-3)
+        t2 = c_lg.topk(2, -1).values
+        print("   causal ids:", c_ids[0].tolist(), " differs from infer() at", int((c_ids != ids_ref).sum()), "of 24 positions;",
+              " min top-2 gap: %.3e" % (t2[..., 0] - t2[..., 1]).min().item())
+        p = torch.zeros(2, 1, 1)
+        for t in range(10):
+            dt_in = torch.cat([p, p[:, :1]], 1)
+            y = adm(tcs[:, :t + 1], dt_in, torch.full((2,), t + 1, dtype=torch.int32))[0][:, -1]
+            p = torch.cat([p, y.reshape(2, 1, 1)], 1)
+        c_raw = p[:, 1:]
+        c_dur = (c_raw + 0.5).to(torch.int32).clamp(1, 128)
+        o_cdur, o_craw = R.adm_infer_causal(R.SD(asd), tcs, acfg, return_raw=True)
+        close("adm causal raw", o_craw, c_raw, 2e-3)
+        assert torch.equal(o_cdur, c_dur), (o_cdur.flatten(), c_dur.flatten())
+        print("   causal durations:", c_dur.flatten().tolist())
+        save("causal_decode", tc8=tc8, plm_ids=c_ids, plm_logits=c_lg, tc_latent=tcs, adm_raw=c_raw, adm_dur=c_dur)
+
         # ---- a12 + a14: the tensor-level body of Megatts.forward (models/megatts2.py:353-368)
         print("Megatts.forward body")
         phone = torch.randint(0, 320, (1, 6), generator=gen(1248))

@@ -338,6 +338,39 @@ def adm_forward(sd, tc_latents, duration_tokens, lens, cfg):
     return F.linear(x, sd("predict_layer.weight"))[..., 0], duration_tokens[:, 1:, 0]
 
 
+# ----------------------------------------------------------------------------- 8f-1 (next row)
+def plm_infer_causal(sd, tc_latent, cfg, return_logits=False):
+    """Checker for the OPT-IN causal decode: greedy loop whose step t takes the last row of the
+    teacher-forced CAUSAL forward (MegaPLM.forward, models/megatts2.py:148-163) over the prefix generated so far.
+    With a causal mask rows < t do not depend on later rows, so this equals a KV-cache decode by construction."""
+    B, T, _ = tc_latent.shape
+    codes = torch.full((B, 1), cfg["vq_bins"], dtype=torch.int64)
+    all_logits = []
+    for t in range(T):
+        pcodes = torch.cat([codes, codes[:, :1]], 1)                      # forward() drops the last column
+        lens = torch.full((B,), t + 1, dtype=torch.int32)
+        lg = plm_forward(sd, tc_latent[:, : t + 1], pcodes, lens, cfg)[0][:, -1]
+        all_logits.append(lg)
+        codes = torch.cat([codes, lg.argmax(-1, keepdim=True)], 1)
+    out = codes[:, 1:]
+    return (out, torch.stack(all_logits, 1)) if return_logits else out
+
+
+def adm_infer_causal(sd, tc_latent, cfg, return_raw=False):
+    """Checker for the OPT-IN causal duration decode: MegaADM.forward's causal stack (models/megatts2.py:233-255)
+    driven with infer()'s raw-float feedback and final rounding (models/megatts2.py:262-275)."""
+    B, T, _ = tc_latent.shape
+    p = torch.zeros(B, 1, 1)
+    for t in range(T):
+        dtok = torch.cat([p, p[:, :1]], 1)                                # forward() drops the last row
+        lens = torch.full((B,), t + 1, dtype=torch.int32)
+        y = adm_forward(sd, tc_latent[:, : t + 1], dtok, lens, cfg)[0][:, -1]
+        p = torch.cat([p, y.reshape(B, 1, 1)], 1)
+    raw = p[:, 1:, :]
+    dur = (raw + 0.5).to(torch.int32).clamp(1, 128)
+    return (dur, raw) if return_raw else dur
+
+
 # ----------------------------------------------------------------------------- a12
 def mel_decode(gsd, tc_latent_expand, p_codes, cfg):
     """Glue + MegaG.decoder of Megatts.forward (models/megatts2.py:361-368)."""

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     from megatts2_b200 import _lib as L
     lib = L.lib()
     syms = _header_symbols()
-    assert len(syms) == 34
+    assert len(syms) == 38
     raw = ctypes.CDLL(L.LIB_PATH)
     for s in syms:
         assert hasattr(raw, s), f"missing export {s}"

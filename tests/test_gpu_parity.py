@@ -455,3 +455,43 @@ def test_batch_invariance_property(weights_cpu, PLM):
     parts = torch.cat([PLM.infer(tc8[:3]), PLM.infer(tc8[3:])], 0)
     assert torch.equal(full, parts)
     assert torch.equal(full, PLM.infer(tc8))                    # deterministic
+
+
+# ------------------------------------------------------------------ opt-in causal KV-cache decode
+def test_causal_decode_golden(golden, PLM, ADM):
+    """Product infer_causal vs the fixture pinned on the real reference's teacher-forced causal forward."""
+    g = golden("causal_decode")
+    ids, logits = PLM.infer_causal(g["tc8"].to(DEV), return_logits=True)
+    assert ids.dtype == torch.int64 and torch.equal(ids.cpu(), g["plm_ids"]), "causal ids must be bit-exact"
+    assert maxerr(logits, g["plm_logits"]) < 2e-3
+    assert torch.equal(PLM.infer_causal(g["tc8"][1:2].to(DEV)).cpu(), g["plm_ids"][1:2])     # batched == per-utterance
+    # self-consistency on the device: ONE teacher-forced pass over the decode's own output reproduces every step
+    pcodes = torch.cat([torch.full((2, 1), 1024, device=DEV), ids], 1)
+    fwd, _ = PLM(g["tc8"].to(DEV), pcodes, torch.tensor([12, 12], dtype=torch.int32, device=DEV))
+    assert maxerr(fwd, logits) < 2e-3 and torch.equal(fwd.argmax(-1), ids)
+    # and it is NOT the reference's infer(): that one is non-causal
+    assert not torch.equal(ids.cpu(), golden("plm")["ids"])
+    dur, raw = ADM.infer_causal(g["tc_latent"].to(DEV), return_raw=True)
+    assert dur.shape == (2, 10, 1) and dur.dtype == torch.int32
+    assert maxerr(raw, g["adm_raw"][..., 0]) < 2e-3
+    assert torch.equal(dur.cpu(), g["adm_dur"])
+
+
+def test_causal_decode_vs_oracle_longer(weights_cpu, PLM, ADM):
+    """Fresh seeded inputs, more steps than the fixture (the K/V cache crosses the 32-key tile of the attention kernel)."""
+    tc8 = F.relu(torch.randn(3, 40, 512, generator=gen(61)))
+    ref_ids, ref_lg = R.plm_infer_causal(R.SD(weights_cpu("plm")), tc8, weights.PLM_CFG, return_logits=True)
+    ids, lg = PLM.infer_causal(tc8.to(DEV), return_logits=True)
+    gap = ref_lg.topk(2, -1).values
+    safe = (gap[..., 0] - gap[..., 1]) > 1e-3            # positions whose argmax is not a numerical coin toss
+    assert safe.float().mean() > 0.9
+    first_bad = (ids.cpu() != ref_ids).float().cumsum(1)
+    assert torch.equal(ids.cpu()[first_bad == 0], ref_ids[first_bad == 0])
+    assert bool((first_bad[:, -1] == 0).all()) or not bool(safe.all()), "ids diverged although every step had a clear margin"
+    if bool((first_bad[:, -1] == 0).all()):
+        assert maxerr(lg, ref_lg) < 3e-3
+    tcl = F.relu(torch.randn(3, 40, 512, generator=gen(62)))
+    ref_dur, ref_raw = R.adm_infer_causal(R.SD(weights_cpu("adm")), tcl, weights.ADM_CFG, return_raw=True)
+    dur, raw = ADM.infer_causal(tcl.to(DEV), return_raw=True)
+    assert maxerr(raw, ref_raw[..., 0]) < 5e-3
+    assert (dur.cpu() != ref_dur).float().mean() < 0.03     # rounding at .5 boundaries only

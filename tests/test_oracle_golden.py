@@ -103,6 +103,19 @@ def test_plm(golden, weights_cpu):
     assert ids.unique().numel() >= 8        # the fixture is not degenerate
 
 
+def test_causal_decode_next_row(golden, weights_cpu):
+    """the opt-in causal decode's checker vs the fixture produced by looping the REAL reference's
+    teacher-forced forward (causal=True).  It is a different function from infer() - the ids differ."""
+    g = golden("causal_decode")
+    ids, lg = R.plm_infer_causal(R.SD(weights_cpu("plm")), g["tc8"], weights.PLM_CFG, return_logits=True)
+    assert torch.equal(ids, g["plm_ids"])
+    assert (lg - g["plm_logits"]).abs().max() < 2e-3
+    assert not torch.equal(ids, golden("plm")["ids"])
+    dur, raw = R.adm_infer_causal(R.SD(weights_cpu("adm")), g["tc_latent"], weights.ADM_CFG, return_raw=True)
+    assert torch.equal(dur, g["adm_dur"])
+    assert (raw - g["adm_raw"]).abs().max() < 2e-3
+
+
 def test_e2e_body(golden, weights_cpu):
     g = golden("e2e")
     o = R.synthesize(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), g["phone"],
