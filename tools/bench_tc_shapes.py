@@ -71,9 +71,6 @@ def main():
         out = torch.empty(s["B"], s["T"], s["Cout"], device=DEV)
         flops = 2.0 * s["B"] * s["T"] * s["Cin"] * s["Cout"] * k
         variants = VARIANTS
-        if os.environ.get("TC_ABLATE"):
-            names = {0: "full", 8: "no global stores", 16: "no tcgen05.ld", 64: "no smem staging", 24: "no ld, no stores", 88: "no ld/stores/staging"}
-            variants = [(f"dbg={d} ({n})", dict(MEGATTS2_TC_PAIR="0", MEGATTS2_TC_SWB64="0", MEGATTS2_TC_DBG=str(d))) for d, n in names.items()]
         for vname, env in variants:
             os.environ.update(env)
             ms = trace_ms(lambda: ops.conv1d(x, wp, b, out=out, w_tc=wt, k=k, dil=dil, pad=pad, pad_mode=1 if k > 1 else 0), reps)
