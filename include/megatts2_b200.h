@@ -155,6 +155,13 @@ int mtts_mel_spectrogram_f32(const float* wav, int64_t wav_sb, int32_t B, int32_
                              const float* window, const float* fb_w, const int32_t* fb_off,
                              const int32_t* fb_start, int32_t n_mels, float clamp_min,
                              float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, void* stream);
+/* Ragged batch for bulk extraction (MelSpecExtractor.extract over a corpus, modules/tokenizer.py:139-155,
+ * prepare_ds.py:211-217): clip b holds lens[b] <= L_max valid samples (device int32); its reflect
+ * padding and frame count 1 + lens[b]/256 follow its own length; frames past that are not written. lens[b] > 512. */
+int mtts_mel_spectrogram_ragged_f32(const float* wav, int64_t wav_sb, int32_t B, int32_t L_max, const int32_t* lens,
+                                    const float* window, const float* fb_w, const int32_t* fb_off,
+                                    const int32_t* fb_start, int32_t n_mels, float clamp_min,
+                                    float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, void* stream);
 
 /* nn.MaxPool1d(k, ceil_mode=True) over time, channels-last (modules/vqpe.py:38,
  * models/megatts2.py:357-358).  x (B, T, C) -> y (B, ceil(T/k), C) */

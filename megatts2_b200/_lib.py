@@ -117,6 +117,7 @@ SIGNATURES = {
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),
     "mtts_vq_gather_f32": (C.c_int, [vp, i32, vp, i32, i32, i32, i32, i32, vp, i64, i32, vp]),
     "mtts_mel_spectrogram_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, i32, f32, vp, i64, i64, i64, vp]),
+    "mtts_mel_spectrogram_ragged_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, vp, vp, vp, i32, f32, vp, i64, i64, i64, vp]),
     "mtts_maxpool_time_f32": (C.c_int, [vp, i64, i32, vp, i64, i32, i32, i32, i32, i32, vp]),
     "mtts_embed_pe_f32": (C.c_int, [vp, i32, vp, i32, i32, vp, f32, i32, i32, i32, vp, i64, i32, vp]),
     "mtts_add_pe_f32": (C.c_int, [vp, i64, i32, vp, f32, i32, i32, i32, vp, i64, i32, vp]),

@@ -105,7 +105,16 @@ int mtts_vq_gather_f32(const int64_t* idx, int32_t idx_ld, const float* embed, i
 int mtts_mel_spectrogram_f32(const float* wav, int64_t wav_sb, int32_t B, int32_t L, const float* window,
                              const float* fb_w, const int32_t* fb_off, const int32_t* fb_start, int32_t n_mels,
                              float clamp_min, float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, void* stream) {
-  return mel_spectrogram(wav, wav_sb, B, L, window, fb_w, fb_off, fb_start, n_mels, clamp_min, out, out_sb, out_sm,
+  return mel_spectrogram(wav, wav_sb, B, L, nullptr, window, fb_w, fb_off, fb_start, n_mels, clamp_min, out, out_sb, out_sm,
+                         out_sf, (cudaStream_t)stream);
+}
+
+int mtts_mel_spectrogram_ragged_f32(const float* wav, int64_t wav_sb, int32_t B, int32_t L_max, const int32_t* lens,
+                                    const float* window, const float* fb_w, const int32_t* fb_off, const int32_t* fb_start,
+                                    int32_t n_mels, float clamp_min, float* out, int64_t out_sb, int64_t out_sm,
+                                    int64_t out_sf, void* stream) {
+  MTTS_REQUIRE(lens, "null lens");
+  return mel_spectrogram(wav, wav_sb, B, L_max, lens, window, fb_w, fb_off, fb_start, n_mels, clamp_min, out, out_sb, out_sm,
                          out_sf, (cudaStream_t)stream);
 }
 

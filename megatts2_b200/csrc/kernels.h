@@ -61,9 +61,9 @@ int length_regulate(const float* x, int64_t x_sb, int ldx, const int32_t* dur, i
                     int L_out, float* y, int64_t y_sb, int ldy, int32_t* totals, cudaStream_t st);
 int copy_strided(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc, float* y, int64_t y_sb, int64_t y_st,
                  int64_t y_sc, int B, int T, int C, int pad_rep, cudaStream_t st);
-int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float* window, const float* fb_w,
-                    const int32_t* fb_off, const int32_t* fb_start, int n_mels, float clamp_min, float* out,
-                    int64_t out_sb, int64_t out_sm, int64_t out_sf, cudaStream_t st);
+int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const int32_t* lens, const float* window,
+                    const float* fb_w, const int32_t* fb_off, const int32_t* fb_start, int n_mels, float clamp_min,
+                    float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, cudaStream_t st);
 // AR-loop helpers
 int plm_build_input(const float* tc, int64_t tc_sb, int tc_ld, int tc_dim, const int64_t* codes, int codes_ld,
                     const float* emb, int vq_dim, int vocab, const float* pe, float alpha, int B, int S, float* X,

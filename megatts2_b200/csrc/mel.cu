@@ -60,7 +60,8 @@ __device__ __forceinline__ void fft8_inplace(float2* v) {
 __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
 
 __global__ void __launch_bounds__(MEL_FPB * 32)
-mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L, int F, const float* __restrict__ window,
+mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32_t* __restrict__ lens,
+           const float* __restrict__ window,
            const float* __restrict__ fb_w, const int32_t* __restrict__ fb_off, const int32_t* __restrict__ fb_start,
            int n_mels, float clamp_min, float* __restrict__ out, int64_t out_sb, int64_t out_sm, int64_t out_sf,
            int vec_ok) {
@@ -76,6 +77,11 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L, int F, const fl
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int b = blockIdx.y;
   const int f0 = blockIdx.x * MEL_FPB;
+  // ragged batches (bulk extraction): clip b holds lens[b] <= L_max valid samples; its reflection and frame
+  // count follow ITS length.  CTA-uniform exit for the frames past a short clip's end.
+  const int L = lens ? min(lens[b], L_max) : L_max;
+  const int F = 1 + L / MEL_HOP;
+  if (f0 >= F || L <= MEL_NFFT / 2) return;
   const float* wv = wav + (int64_t)b * wav_sb;
   const int g0 = f0 * MEL_HOP - MEL_NFFT / 2;
   // stage the CTA's sample span.  Interior tiles (no reflection, 16-byte aligned) use batched float4 loads so
@@ -212,9 +218,9 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L, int F, const fl
 static std::mutex g_mel_mu;
 static bool g_mel_ready[64] = {false};
 
-int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float* window, const float* fb_w,
-                    const int32_t* fb_off, const int32_t* fb_start, int n_mels, float clamp_min, float* out,
-                    int64_t out_sb, int64_t out_sm, int64_t out_sf, cudaStream_t st) {
+int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const int32_t* lens, const float* window,
+                    const float* fb_w, const int32_t* fb_off, const int32_t* fb_start, int n_mels, float clamp_min,
+                    float* out, int64_t out_sb, int64_t out_sm, int64_t out_sf, cudaStream_t st) {
   MTTS_REQUIRE(wav && window && fb_w && fb_off && fb_start && out, "null pointer");
   MTTS_REQUIRE(L > MEL_NFFT / 2, "reflect padding needs L > n_fft/2 (torch.stft center=True)");
   MTTS_REQUIRE(n_mels > 0 && n_mels <= 128, "n_mels out of range");
@@ -243,8 +249,9 @@ int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const float*
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     dim3 grid((unsigned)cdiv64(F, MEL_FPB), (unsigned)nb);
-    mel_kernel<<<grid, MEL_FPB * 32, smem, st>>>(wav + (int64_t)b0 * wav_sb, wav_sb, L, F, window, fb_w, fb_off, fb_start,
-                                               n_mels, clamp_min, out + (int64_t)b0 * out_sb, out_sb, out_sm, out_sf, vec_ok);
+    mel_kernel<<<grid, MEL_FPB * 32, smem, st>>>(wav + (int64_t)b0 * wav_sb, wav_sb, L, lens ? lens + b0 : nullptr, window, fb_w,
+                                               fb_off, fb_start, n_mels, clamp_min, out + (int64_t)b0 * out_sb, out_sb, out_sm,
+                                               out_sf, vec_ok);
     MTTS_CHECK_LAUNCH();
   }
   return 0;

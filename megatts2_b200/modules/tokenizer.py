@@ -71,3 +71,49 @@ def extract_mel_spec(samples: torch.Tensor, frames_major: bool = False) -> torch
     out = ops.mel_spectrogram(x, t["window"], t["fb_w"], t["fb_off"], t["fb_start"], HIFIGAN_MEL_CHANNELS, 1e-5,
                               frames_major=frames_major)
     return out[0] if squeeze else out
+
+
+def compute_num_frames(num_samples: int, hop: int = HIFIGAN_HOP_LENGTH) -> int:
+    """Frames the reference keeps per clip: ``lhotse.utils.compute_num_frames(duration, frame_shift, sr)``
+    (modules/tokenizer.py:149-154; lhotse is an un-vendored, unpinned dependency of the reference - restated from its
+    published definition, parity unpinned).  With duration = L / sr and frame_shift = hop / sr both of lhotse's forms
+    (round-half-up of duration / frame_shift; (samples + hop // 2) // hop) reduce to this integer expression."""
+    return (int(num_samples) + hop // 2) // hop
+
+
+class MelSpecExtractor:
+    """Bulk mel extraction with the surface of the reference's lhotse extractor (modules/tokenizer.py:128-155;
+    caller prepare_ds.py:211-217): ``extract(samples, sampling_rate) -> (num_frames, 80)`` numpy, plus
+    ``extract_batch`` which runs a whole list of ragged clips as ONE kernel launch.
+    The lhotse base class / HDF5 writer plumbing stays the reference's."""
+    name = "mel_spec"
+    frame_shift = HIFIGAN_HOP_LENGTH / HIFIGAN_SR
+
+    def __init__(self, device="cuda"):
+        self.device = torch.device(device)
+
+    def feature_dim(self, sampling_rate: int) -> int:
+        return HIFIGAN_MEL_CHANNELS
+
+    def extract(self, samples, sampling_rate: int) -> np.ndarray:
+        return self.extract_batch([samples], sampling_rate)[0]
+
+    def extract_batch(self, clips, sampling_rate: int = HIFIGAN_SR):
+        assert sampling_rate == HIFIGAN_SR
+        clips = [torch.as_tensor(np.asarray(c) if not isinstance(c, torch.Tensor) else c, dtype=torch.float32).squeeze()
+                 for c in clips]
+        if not clips:
+            return []
+        lens = [int(c.shape[-1]) for c in clips]
+        if min(lens) <= HIFIGAN_NFFT // 2:
+            raise ValueError("clips must be longer than n_fft / 2 samples (reflect padding, as torch.stft)")
+        L_max = (max(lens) + 3) // 4 * 4                         # 16-byte aligned rows for the vector loads
+        host = torch.zeros(len(clips), L_max, dtype=torch.float32, pin_memory=self.device.type == "cuda")
+        for i, c in enumerate(clips):
+            host[i, :lens[i]] = c
+        wav = host.to(self.device, non_blocking=True)
+        lens_d = torch.tensor(lens, dtype=torch.int32, device=self.device)
+        t = _MelTables.get(wav.device)
+        mel = ops.mel_spectrogram(wav, t["window"], t["fb_w"], t["fb_off"], t["fb_start"], HIFIGAN_MEL_CHANNELS, 1e-5,
+                                  frames_major=True, lens=lens_d).cpu().numpy()      # (B, F_max, 80)
+        return [mel[i, :compute_num_frames(lens[i])] for i in range(len(clips))]

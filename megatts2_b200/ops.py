@@ -257,22 +257,31 @@ def to_channels_first(x_btc):
     return y
 
 
-def mel_spectrogram(wav, window, fb_w, fb_off, fb_start, n_mels=80, clamp=1e-5, frames_major=False):
-    """wav (B, L) -> (B, n_mels, F) or (B, F, n_mels) if frames_major; F = 1 + L // 256."""
+def mel_spectrogram(wav, window, fb_w, fb_off, fb_start, n_mels=80, clamp=1e-5, frames_major=False, lens=None):
+    """wav (B, L) -> (B, n_mels, F) or (B, F, n_mels) if frames_major; F = 1 + L // 256.
+    ``lens`` (B,) int32 on the device: ragged batch, clip b is wav[b, :lens[b]]; frames past 1 + lens[b] // 256 are
+    left at zero."""
     wav = _dev(wav, name="wav")
     if wav.stride(1) != 1:
         wav = wav.contiguous()
     B, Lw = wav.shape
     F = 1 + Lw // 256
+    alloc = torch.zeros if lens is not None else torch.empty
     if frames_major:
-        out = torch.empty(B, F, n_mels, dtype=_F32, device=wav.device)
+        out = alloc(B, F, n_mels, dtype=_F32, device=wav.device)
         sb, sm, sf = out.stride(0), 1, out.stride(1)
     else:
-        out = torch.empty(B, n_mels, F, dtype=_F32, device=wav.device)
+        out = alloc(B, n_mels, F, dtype=_F32, device=wav.device)
         sb, sm, sf = out.stride(0), out.stride(1), 1
-    L.check(L.lib().mtts_mel_spectrogram_f32(_ptr(wav), wav.stride(0), B, Lw, _ptr(_dev(window)), _ptr(_dev(fb_w)),
-                                             _ptr(_dev(fb_off, torch.int32)), _ptr(_dev(fb_start, torch.int32)),
-                                             n_mels, clamp, _ptr(out), sb, sm, sf, _stream()))
+    tabs = (_ptr(_dev(window)), _ptr(_dev(fb_w)), _ptr(_dev(fb_off, torch.int32)), _ptr(_dev(fb_start, torch.int32)))
+    if lens is None:
+        L.check(L.lib().mtts_mel_spectrogram_f32(_ptr(wav), wav.stride(0), B, Lw, *tabs, n_mels, clamp, _ptr(out), sb, sm, sf,
+                                                 _stream()))
+    else:
+        lens = _dev(lens, torch.int32, name="lens")
+        assert lens.shape == (B,) and lens.is_contiguous()
+        L.check(L.lib().mtts_mel_spectrogram_ragged_f32(_ptr(wav), wav.stride(0), B, Lw, _ptr(lens), *tabs, n_mels, clamp,
+                                                        _ptr(out), sb, sm, sf, _stream()))
     return out
 
 

@@ -23,7 +23,7 @@ def test_library_exports_every_declared_symbol():
     from megatts2_b200 import _lib as L
     lib = L.lib()
     syms = _header_symbols()
-    assert len(syms) == 38
+    assert len(syms) == 39
     raw = ctypes.CDLL(L.LIB_PATH)
     for s in syms:
         assert hasattr(raw, s), f"missing export {s}"
@@ -173,3 +173,16 @@ def test_hifigan_state_dict_matches_oracle_spec():
     spec = weights.hifigan_spec()
     assert set(sd.keys()) == set(spec.keys())
     assert all(tuple(sd[k].shape) == tuple(spec[k]) for k in spec)
+
+
+def test_compute_num_frames_matches_both_lhotse_forms():
+    """modules/tokenizer.py:149-154 truncates to lhotse's compute_num_frames; both published forms of it
+    (Decimal round-half-up of duration / frame_shift, and (samples + hop // 2) // hop) agree with ours."""
+    from decimal import ROUND_HALF_UP, Decimal
+    from megatts2_b200.modules.tokenizer import compute_num_frames
+    sr, hop = 16000, 256
+    for n in list(range(513, 3000, 37)) + [47872, 47873, 48000, 48127, 48128, 160000, 1234567]:
+        duration = round(n / sr, ndigits=12)
+        form_a = int(Decimal(round(duration / (hop / sr), ndigits=8)).quantize(0, rounding=ROUND_HALF_UP))
+        form_b = (n + hop // 2) // hop
+        assert compute_num_frames(n) == form_a == form_b, n

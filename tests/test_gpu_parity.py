@@ -7,6 +7,7 @@ summation order; the noise floors are in SURVEY.md §7.2)."""
 import math
 import os
 
+import numpy as np
 import pytest
 import torch
 import torch.nn.functional as F
@@ -495,3 +496,23 @@ def test_causal_decode_vs_oracle_longer(weights_cpu, PLM, ADM):
     dur, raw = ADM.infer_causal(tcl.to(DEV), return_raw=True)
     assert maxerr(raw, ref_raw[..., 0]) < 5e-3
     assert (dur.cpu() != ref_dur).float().mean() < 0.03     # rounding at .5 boundaries only
+
+
+# ------------------------------------------------------------------ bulk (ragged) mel extraction
+def test_mel_extractor_ragged_batch_vs_oracle():
+    """MelSpecExtractor.extract_batch: ragged clips in ONE launch == the oracle clip by clip, truncated to the
+    reference's compute_num_frames (modules/tokenizer.py:139-155)."""
+    from megatts2_b200.modules.tokenizer import MelSpecExtractor, compute_num_frames
+    ex = MelSpecExtractor(DEV)
+    lens = [48000, 16000, 5000, 777, 47873, 2816, 2817, 24321]       # incl. lengths on either side of tile / hop edges
+    clips = [(torch.rand(n, generator=gen(100 + i)) * 2 - 1) for i, n in enumerate(lens)]
+    outs = ex.extract_batch([c.numpy() for c in clips], 16000)
+    for c, o, n in zip(clips, outs, lens):
+        ref = R.mel_spectrogram(c.unsqueeze(0))[0].transpose(0, 1)[: compute_num_frames(n)]    # (frames, 80)
+        assert o.shape == (compute_num_frames(n), 80) == tuple(ref.shape)
+        assert float(np.abs(o - ref.numpy()).max()) < 1e-4
+        assert float(np.abs(o - ref.numpy()).mean()) < 1e-5
+    one = ex.extract(clips[3].numpy(), 16000)                              # single clip == its row of the batch
+    assert np.array_equal(one, outs[3])
+    with pytest.raises(ValueError):
+        ex.extract(np.zeros(512, dtype=np.float32), 16000)                 # reflect padding needs L > n_fft / 2
