@@ -59,7 +59,7 @@ __device__ __forceinline__ void fft8_inplace(float2* v) {
 }
 __device__ __forceinline__ int zpad(int i) { return i + (i >> 3); }
 
-__global__ void __launch_bounds__(MEL_FPB * 32)
+__global__ void __launch_bounds__(MEL_FPB * 32, 3)
 mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32_t* __restrict__ lens,
            const float* __restrict__ window,
            const float* __restrict__ fb_w, const int32_t* __restrict__ fb_off, const int32_t* __restrict__ fb_start,
@@ -144,20 +144,39 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32
       z[zpad(idx + 0)] = v[h][0]; z[zpad(idx + 1)] = v[h][4]; z[zpad(idx + 2)] = v[h][2]; z[zpad(idx + 3)] = v[h][6];
       z[zpad(idx + 4)] = v[h][1]; z[zpad(idx + 5)] = v[h][5]; z[zpad(idx + 6)] = v[h][3]; z[zpad(idx + 7)] = v[h][7];
     }
-    __syncwarp();
-    // ---- pass 1 (Ns = 8) and pass 2 (Ns = 64)
+    // ---- pass 1 (Ns = 8) and pass 2 (Ns = 64).  Twiddles w^(r*k): k = j & (Ns-1).  For Ns = 8 both halves of a lane
+    // (j = lane, lane + 32) share k; for Ns = 64 the second half's twiddle is the first half's times exp(-2 pi i r/16),
+    // a compile-time constant - so a lane fetches 7 table entries per pass (not 14), and fetches them BEFORE the
+    // warp barrier that precedes the pass so their latency overlaps the exchange through shared memory.
 #pragma unroll
     for (int pass = 1; pass < 3; ++pass) {
       const int Ns = (pass == 1) ? 8 : 64;
       const int tws = (pass == 1) ? 16 : 2;   // g_tw1024 index step: 2 * 512 / (Ns * 8)
+      float2 tw[8];
+      {
+        const int k0 = lane & (Ns - 1);
+#pragma unroll
+        for (int r = 1; r < 8; ++r) tw[r] = g_tw1024[r * k0 * tws];
+      }
+      __syncwarp();   // the previous pass's stores are visible
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         const int j = lane + 32 * h;
-        const int k = j & (Ns - 1);
 #pragma unroll
         for (int r = 0; r < 8; ++r) {
           float2 a = z[zpad(j + 64 * r)];
-          if (r > 0) a = cmul(a, g_tw1024[r * k * tws]);
+          if (r > 0) {
+            float2 t = tw[r];
+            if (pass == 2 && h == 1) {
+              // exp(-2 pi i r / 16), r = 1..7
+              constexpr float C16[8] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.f,
+                                        -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f};
+              constexpr float S16[8] = {0.f, -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.f,
+                                        -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+              t = cmul(t, make_float2(C16[r], S16[r]));
+            }
+            a = cmul(a, t);
+          }
           v[h][r] = a;
         }
         fft8_inplace(v[h]);
@@ -171,8 +190,8 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32
         z[zpad(idx + 3 * Ns)] = v[h][6]; z[zpad(idx + 4 * Ns)] = v[h][1]; z[zpad(idx + 5 * Ns)] = v[h][5];
         z[zpad(idx + 6 * Ns)] = v[h][3]; z[zpad(idx + 7 * Ns)] = v[h][7];
       }
-      __syncwarp();
     }
+    __syncwarp();
     // ---- untangle the packed real transform: bins k and 512-k from Z[k], Z[512-k]
     for (int k = lane; k <= 256; k += 32) {
       if (k == 0) {
@@ -194,8 +213,22 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32
     __syncwarp();
     for (int m = lane; m < n_mels; m += 32) {
       const int o0 = fb_off[m], o1 = fb_off[m + 1], s0 = fb_start[m];
-      float acc = 0.f;
-      for (int i = o0; i < o1; ++i) acc = fmaf(mg[s0 + (i - o0)], i < 1536 ? fbw_s[i] : __ldg(fb_w + i), acc);
+      // four independent partial sums: the single-accumulator form was one dependent LDS -> FMA chain per tap
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+      const float* mgp = mg + s0 - o0;
+      int i = o0;
+      if (o1 <= 1536) {
+        for (; i + 4 <= o1; i += 4) {
+          a0 = fmaf(mgp[i], fbw_s[i], a0);
+          a1 = fmaf(mgp[i + 1], fbw_s[i + 1], a1);
+          a2 = fmaf(mgp[i + 2], fbw_s[i + 2], a2);
+          a3 = fmaf(mgp[i + 3], fbw_s[i + 3], a3);
+        }
+        for (; i < o1; ++i) a0 = fmaf(mgp[i], fbw_s[i], a0);
+      } else {
+        for (; i < o1; ++i) a0 = fmaf(mgp[i], i < 1536 ? fbw_s[i] : __ldg(fb_w + i), a0);
+      }
+      const float acc = (a0 + a1) + (a2 + a3);
       otile[m * MEL_FPB + w] = logf(fmaxf(acc, clamp_min));
     }
   }
