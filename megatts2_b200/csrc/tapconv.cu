@@ -350,9 +350,11 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st) {
   {
     const int64_t tiles64 = cdiv64(M, 64) * cdiv64(p.Cout, 64);
     const int nk = (p.Cin + 15) / 16;
-    if (p.k == 1 && p.stride == 1 && p.pad == 0 && p.out_shift == 0 && !p.in_lens && M <= 256 && tiles64 <= 74 &&
+    if (p.k == 1 && p.stride == 1 && p.pad == 0 && p.out_shift == 0 && !p.in_lens && M <= 256 && tiles64 <= 148 &&
         nk >= 16 && p.tc_scratch) {
-      int splits = (int)(148 / tiles64);
+      // two CTAs per SM: a lone 8-warp CTA cannot hide the L2 latency of its one-chunk-ahead prefetch
+      static const int target = []() { const char* e = getenv("MEGATTS2_SPLITK_CTAS"); return e ? atoi(e) : 296; }();
+      int splits = (int)(target / tiles64);
       if (splits > 16) splits = 16;
       if (splits > nk / 4) splits = nk / 4;
       if (splits >= 2 && (int64_t)splits * M * p.Cout * 4 + 256 <= p.tc_scratch_bytes) {
