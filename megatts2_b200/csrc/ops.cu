@@ -172,20 +172,21 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
 
 // ------------------------------------------------------------------------------------------
 // Attention, fp32, online softmax.  CTA = NW warps x RW query rows of one (b, h); K/V stream through
-// shared memory 32 keys at a time (float4 global loads when aligned); lane l scores key l, then owns
+// shared memory 32*KPL keys at a time (float4 global loads when aligned); lane l scores keys l (+32 when KPL = 2:
+// the broadcast Q loads of the score loop are then shared by two keys - that loop is shared-memory-bound), then owns
 // output dims l + 32*i.  Head dims on the path: 64 (PLM), 96 (ADM), 256 (phone encoder), 512 (MRTE
 // cross-attention, Tk ~ 32).  For dh <= 128 a CTA covers 64 query rows, i.e. a whole AR-step sequence:
 // K and V are read once per (b, h).
-template <int NI, int RW, int NW>
+template <int NI, int RW, int NW, int KPL>
 __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p, const int vec) {
   constexpr int DH = 32 * NI;
-  constexpr int BQ = RW * NW, BKV = 32, NT = NW * 32;
+  constexpr int BQ = RW * NW, BKV = 32 * KPL, NT = NW * 32;
   extern __shared__ __align__(16) float sm[];
   float* Qs = sm;                        // [BQ][DH]
   constexpr int KS = DH + 4;             // K row stride: 16-byte aligned rows, conflict-free 128-bit reads (lane stride 4 banks)
   float* Ks = Qs + BQ * DH;              // [BKV][KS]
   float* Vs = Ks + BKV * KS;             // [BKV][DH]
-  float* Ps = Vs + BKV * DH;             // [NW][RW][32]
+  float* Ps = Vs + BKV * DH;             // [NW][RW][BKV]
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int q0 = blockIdx.x * BQ, h = blockIdx.y, b = blockIdx.z;
   const float* qb = p.q + (int64_t)b * p.q_sb + (int64_t)h * DH;
@@ -244,48 +245,67 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
     }
     __syncthreads();
     if (!warp_live) continue;
-    float s[RW];
+    float s[RW][KPL];
 #pragma unroll
-    for (int i = 0; i < RW; ++i) s[i] = 0.f;
-    // 128-bit shared loads: one K chunk per lane + RW broadcast Q chunks feed 4 * RW FMAs (the scalar form issued
-    // 9 loads per 8 FMAs and was load-issue bound); the d order of every dot product is unchanged
+    for (int i = 0; i < RW; ++i)
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) s[i][c] = 0.f;
+    // 128-bit shared loads: KPL key chunks per lane + RW broadcast Q chunks feed 4 * RW * KPL FMAs (the scalar form
+    // issued 9 loads per 8 FMAs and was load-issue bound); the d order of every dot product is unchanged
     const float* kr = Ks + lane * KS;
     const float* qr = Qs + (w * RW) * DH;
 #pragma unroll 4
     for (int d = 0; d < DH; d += 4) {
-      const float4 kv = *reinterpret_cast<const float4*>(kr + d);
+      float4 kv[KPL];
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) kv[c] = *reinterpret_cast<const float4*>(kr + c * 32 * KS + d);
 #pragma unroll
       for (int i = 0; i < RW; ++i) {
         const float4 qv = *reinterpret_cast<const float4*>(qr + i * DH + d);
-        s[i] = fmaf(qv.x, kv.x, s[i]);
-        s[i] = fmaf(qv.y, kv.y, s[i]);
-        s[i] = fmaf(qv.z, kv.z, s[i]);
-        s[i] = fmaf(qv.w, kv.w, s[i]);
+#pragma unroll
+        for (int c = 0; c < KPL; ++c) {
+          s[i][c] = fmaf(qv.x, kv[c].x, s[i][c]);
+          s[i][c] = fmaf(qv.y, kv[c].y, s[i][c]);
+          s[i][c] = fmaf(qv.z, kv[c].z, s[i][c]);
+          s[i][c] = fmaf(qv.w, kv[c].w, s[i][c]);
+        }
       }
     }
-    const bool kvalid = (k0 + lane) < p.Tk;
 #pragma unroll
     for (int i = 0; i < RW; ++i) {
-      float v = s[i] * p.scale;
-      if (mrow[i]) v += kvalid ? mrow[i][k0 + lane] : 0.f;
-      v = kvalid ? v : -INFINITY;
-      const float m_new = fmaxf(m_run[i], warp_max(v));
+      float v[KPL];
+      float vmax = -INFINITY;
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) {
+        const int key = k0 + lane + 32 * c;
+        const bool kvalid = key < p.Tk;
+        float x = s[i][c] * p.scale;
+        if (mrow[i]) x += kvalid ? mrow[i][key] : 0.f;
+        v[c] = kvalid ? x : -INFINITY;
+        vmax = fmaxf(vmax, v[c]);
+      }
+      const float m_new = fmaxf(m_run[i], warp_max(vmax));
       const float m_use = (m_new == -INFINITY) ? 0.f : m_new;
-      const float pr = expf(v - m_use);
+      float psum = 0.f;
+#pragma unroll
+      for (int c = 0; c < KPL; ++c) {
+        const float pr = expf(v[c] - m_use);
+        Ps[(w * RW + i) * BKV + lane + 32 * c] = pr;
+        psum += pr;
+      }
       const float alpha = expf(m_run[i] - m_use);
-      l_run[i] = l_run[i] * alpha + warp_sum(pr);
+      l_run[i] = l_run[i] * alpha + warp_sum(psum);
       m_run[i] = m_new;
 #pragma unroll
       for (int j = 0; j < NI; ++j) acc[i][j] *= alpha;
-      Ps[(w * RW + i) * 32 + lane] = pr;
     }
     __syncwarp();
-    const float* pw = Ps + (w * RW) * 32;
+    const float* pw = Ps + (w * RW) * BKV;
 #pragma unroll 2
     for (int j = 0; j < BKV; j += 4) {
       float4 pj[RW];
 #pragma unroll
-      for (int i = 0; i < RW; ++i) pj[i] = *reinterpret_cast<const float4*>(pw + i * 32 + j);
+      for (int i = 0; i < RW; ++i) pj[i] = *reinterpret_cast<const float4*>(pw + i * BKV + j);
 #pragma unroll
       for (int ii = 0; ii < NI; ++ii) {
         const float v0 = Vs[(j + 0) * DH + lane + 32 * ii], v1 = Vs[(j + 1) * DH + lane + 32 * ii];
@@ -336,14 +356,14 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
   }
 }
 
-template <int NI, int RW, int NW>
+template <int NI, int RW, int NW, int KPL = 1>
 static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   constexpr int DH = 32 * NI;
-  constexpr int BQ = RW * NW;
-  const size_t smem = sizeof(float) * (BQ * DH + 32 * (DH + 4) + 32 * DH + NW * RW * 32);
+  constexpr int BQ = RW * NW, BKV = 32 * KPL;
+  const size_t smem = sizeof(float) * (BQ * DH + BKV * (DH + 4) + BKV * DH + NW * RW * BKV);
   static bool configured = false;   // per-process, per-instantiation; attribute set is idempotent
   if (!configured) {
-    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI, RW, NW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI, RW, NW, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "attention", (long long)e);
     configured = true;
   }
@@ -351,7 +371,7 @@ static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   const int vec = al(p.q) && al(p.k) && al(p.v) && p.q_st % 4 == 0 && p.k_st % 4 == 0 && p.v_st % 4 == 0 &&
                   p.q_sb % 4 == 0 && p.k_sb % 4 == 0 && p.v_sb % 4 == 0;
   dim3 grid((unsigned)cdiv64(p.Tq, BQ), (unsigned)p.H, (unsigned)p.B);
-  attn_kernel<NI, RW, NW><<<grid, NW * 32, smem, st>>>(p, vec);
+  attn_kernel<NI, RW, NW, KPL><<<grid, NW * 32, smem, st>>>(p, vec);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -362,12 +382,29 @@ int attention(const mtts_attn_params& p, cudaStream_t st) {
   MTTS_REQUIRE(p.B >= 0 && p.H > 0 && p.Tq >= 0 && p.Tk > 0, "bad dims");
   MTTS_REQUIRE(p.H <= 65535 && p.B <= 65535, "grid too large");
   if (p.B == 0 || p.Tq == 0) return 0;
+  // dh <= 128: one CTA of 8 warps covers a whole AR-step sequence (Tq <= 64), so K and V are read once per (b, h);
+  // the rows are dealt evenly to the warps (RW = ceil(Tq / 8) rows each) - with a fixed 8 rows per warp a 35-row
+  // step left three of the eight warps idle.  Row results do not depend on RW (each row's sums keep their order).
+  if (p.dh == 64 || p.dh == 96 || p.dh == 128) {
+    const int rw = p.Tq >= 64 ? 8 : (p.Tq + 7) / 8;
+    const bool two = p.Tk > 32;          // two keys per lane: one 64-key tile instead of two 32-key tiles
+#define MTTS_ATTN_RW(NI)                                                                    \
+    switch (rw) {                                                                             \
+      case 1: return two ? attn_launch<NI, 1, 8, 2>(p, st) : attn_launch<NI, 1, 8>(p, st);    \
+      case 2: return two ? attn_launch<NI, 2, 8, 2>(p, st) : attn_launch<NI, 2, 8>(p, st);    \
+      case 3: return two ? attn_launch<NI, 3, 8, 2>(p, st) : attn_launch<NI, 3, 8>(p, st);    \
+      case 4: return two ? attn_launch<NI, 4, 8, 2>(p, st) : attn_launch<NI, 4, 8>(p, st);    \
+      case 5: return two ? attn_launch<NI, 5, 8, 2>(p, st) : attn_launch<NI, 5, 8>(p, st);    \
+      case 6: return two ? attn_launch<NI, 6, 8, 2>(p, st) : attn_launch<NI, 6, 8>(p, st);    \
+      case 7: return two ? attn_launch<NI, 7, 8, 2>(p, st) : attn_launch<NI, 7, 8>(p, st);    \
+      default: return two ? attn_launch<NI, 8, 8, 2>(p, st) : attn_launch<NI, 8, 8>(p, st);   \
+    }
+    if (p.dh == 64) { MTTS_ATTN_RW(2) }
+    if (p.dh == 96) { MTTS_ATTN_RW(3) }
+    MTTS_ATTN_RW(4)
+#undef MTTS_ATTN_RW
+  }
   switch (p.dh) {
-    // dh <= 128: 64 query rows per CTA when the sequence is longer than 16 rows; single-row (AR last position)
-    // and short sequences keep the 16-row CTA
-    case 64: return p.Tq > 16 ? attn_launch<2, 8, 8>(p, st) : attn_launch<2, 4, 4>(p, st);
-    case 96: return p.Tq > 16 ? attn_launch<3, 8, 8>(p, st) : attn_launch<3, 4, 4>(p, st);
-    case 128: return p.Tq > 16 ? attn_launch<4, 8, 8>(p, st) : attn_launch<4, 4, 4>(p, st);
     case 256: return attn_launch<8, 4, 4>(p, st);
     case 512: return attn_launch<16, 4, 4>(p, st);
     default: return fail(MTTS_ERR_UNSUPPORTED, "%s: head dim %lld not in {64,96,128,256,512}", "attention", p.dh);
