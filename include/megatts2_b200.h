@@ -95,6 +95,10 @@ typedef struct {
   int32_t tc_presplit;
   void* tc_out_planes; int64_t tc_out_plane_stride;
   int32_t tc_out_ld, tc_out_tp, tc_out_hl, tc_out_act; float tc_out_slope;
+  /* optional room for split-K partial sums (tensor-core engine, k == 1): when a dense layer has too few output tiles to
+   * fill the GPU, K is split across CTAs into fp32 partials here and a second kernel reduces them in a fixed order and
+   * applies the epilogue.  >= splits * B*Tout * Cout * 4 bytes; NULL -> never split. */
+  void* tc_partial; int64_t tc_partial_bytes;
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);

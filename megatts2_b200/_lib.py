@@ -32,6 +32,7 @@ class ConvParams(C.Structure):
         ("w_tc", vp), ("tc_scratch", vp), ("tc_scratch_bytes", i64), ("tc_rows_cap", i64),
         ("tc_presplit", i32), ("tc_out_planes", vp), ("tc_out_plane_stride", i64),
         ("tc_out_ld", i32), ("tc_out_tp", i32), ("tc_out_hl", i32), ("tc_out_act", i32), ("tc_out_slope", f32),
+        ("tc_partial", vp), ("tc_partial_bytes", i64),
     ]
 
 

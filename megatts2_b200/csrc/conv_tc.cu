@@ -32,6 +32,8 @@ struct ConvTcArgs {
   int64_t out_shift, ybe;      // transposed-conv form: element offset of the output and valid range per batch item
   // optional bf16x3 copy of the result for the next tensor-core layer
   __nv_bfloat16* op; int64_t op_stride; int32_t op_ld, op_tp, op_hl, op_act; float op_slope;
+  // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
+  int32_t splits; float* partial;
 };
 
 // PAIR = 1: two CTAs of a cluster run one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of
@@ -72,7 +74,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int num_t = (g.T + BM - 1) / BM, num_n = (g.Cout + BN - 1) / BN;
-  const int num_tiles = g.B * num_t * num_n;
+  const int num_tiles = g.B * num_t * num_n * g.splits;      // work items: (tile, K split)
   const int ncb = (g.Cin + Cfg::BK - 1) / Cfg::BK;
   const int num_k = g.k * ncb;
 
@@ -116,11 +118,13 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     // bulk copies of a K-slab (A p0..p2, B p0..p2) so the copies are issued concurrently - with one issuing
     // thread the ~6 x 100-150 cycles of issue latency per slab bound the small-channel convs
     int stage = 0, phase = 0;
-    for (int tile = worker; tile < num_tiles; tile += nworkers) {
+    for (int item = worker; item < num_tiles; item += nworkers) {
+      const int sp = item % g.splits, tile = item / g.splits;
+      const int kb0 = (int)((int64_t)sp * num_k / g.splits), kb1 = (int)((int64_t)(sp + 1) * num_k / g.splits);
       const int nb = tile % num_n, r = tile / num_n;
       const int tb = r % num_t, b = r / num_t;
       const int trow = tb * BM + (int)crank * 128;               // this CTA's first output row
-      for (int kb = 0; kb < num_k; ++kb) {
+      for (int kb = kb0; kb < kb1; ++kb) {
         const int j = kb / ncb, cb = kb - j * ncb;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_base + stage * Cfg::STAGE;
@@ -149,19 +153,21 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
       const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint64_t desc_base = umma_desc_kmajor<SWB>(0u);      // everything except the start address
       int stage = 0, phase = 0, it = 0;
-      for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+      for (int item = worker; item < num_tiles; item += nworkers, ++it) {
+        const int sp = item % g.splits;
+        const int kb0 = (int)((int64_t)sp * num_k / g.splits), kb1 = (int)((int64_t)(sp + 1) * num_k / g.splits);
         const int as = it % NACC, aphase = (it / NACC) & 1;
         mbar_wait(tempty_bar + 8 * as, aphase ^ 1);        // the epilogue (of both CTAs) has drained this buffer
         tc_fence_after();
         const uint32_t d_main = tmem_base + as * (2 * BN);
         const uint32_t d_corr = d_main + BN;
-        for (int kb = 0; kb < num_k; ++kb) {
+        for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
           // descriptors: constant high word, low word = (smem address >> 4); planes / k-steps are plain adds
           const uint64_t a0 = desc_base | (uint64_t)(((smem_base + stage * Cfg::STAGE) >> 4) & 0x3FFF);
           const uint64_t b0 = a0 + (3 * Cfg::A_PLANE >> 4);
-          const uint32_t first = (kb == 0) ? 0u : 1u;
+          const uint32_t first = (kb == kb0) ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
             const uint64_t a1 = a0 + 2 * ks, a2 = a1 + (Cfg::A_PLANE >> 4), a3 = a2 + (Cfg::A_PLANE >> 4);
@@ -185,10 +191,10 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
           }
           if constexpr (PAIR) {
             tc_commit_2sm(empty_bar + 8 * stage);          // frees the stage in both CTAs
-            if (kb == num_k - 1) tc_commit_2sm(tfull_bar + 8 * as);
+            if (kb == kb1 - 1) tc_commit_2sm(tfull_bar + 8 * as);
           } else {
             tc_commit(empty_bar + 8 * stage);
-            if (kb == num_k - 1) tc_commit(tfull_bar + 8 * as);
+            if (kb == kb1 - 1) tc_commit(tfull_bar + 8 * as);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -202,7 +208,8 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
     const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
     int it = 0;
-    for (int tile = worker; tile < num_tiles; tile += nworkers, ++it) {
+    for (int item = worker; item < num_tiles; item += nworkers, ++it) {
+      const int sp = item % g.splits, tile = item / g.splits;
       const int nb = tile % num_n, r0 = tile / num_n;
       const int tb = r0 % num_t, b = r0 / num_t;
       const int as = it % NACC, aphase = (it / NACC) & 1;
@@ -220,12 +227,12 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
         const bool ncol = n < g.Cout;                 // Cout % 4 == 0: a 4-wide chunk is all-in or all-out
         // independent global loads first (bias once per lane; residual / accumulate per owned row)
         float4 bvec = make_float4(0.f, 0.f, 0.f, 0.f), rv[4], ov[4];
-        if (ncol && g.bias) bvec = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        if (ncol && g.bias && g.splits == 1) bvec = __ldg(reinterpret_cast<const float4*>(g.bias + n));
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int tt = t_base + i * 8 + rsub;
           rv[i] = ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ncol && tt < g.T && !g.out_shift) {
+          if (ncol && tt < g.T && !g.out_shift && g.splits == 1) {
             if (g.res) rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
             if (g.accumulate) ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
           }
@@ -253,6 +260,10 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
           const int row = i * 8 + rsub, tt = t_base + row;
           if (!ncol || tt >= g.T) continue;
           const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 20 + chunk * 4);
+          if (g.splits > 1) {      // raw partial sums; bias / activation / residual run in the reduction kernel
+            *reinterpret_cast<float4*>(g.partial + (((int64_t)sp * g.B + b) * g.T + tt) * g.Cout + n) = a4;
+            continue;
+          }
           float v[4] = {a4.x + bvec.x, a4.y + bvec.y, a4.z + bvec.z, a4.w + bvec.w};
           if (g.post_act != MTTS_ACT_NONE) {
 #pragma unroll
@@ -298,6 +309,48 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// split-K reduction: sums the partial tiles in a FIXED order (bit-reproducible) and applies the tap-GEMM epilogue
+// (bias -> activation -> residual -> scale -> accumulate -> fp32 and/or bf16x3 plane store)
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_kernel(const ConvTcArgs g, int64_t total4) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total4) return;
+  const int c4 = g.Cout / 4;
+  const int n = (int)(i % c4) * 4;
+  const int64_t row = i / c4;                 // b * T + t
+  const int b = (int)(row / g.T), tt = (int)(row - (int64_t)b * g.T);
+  const int64_t stride = (int64_t)g.B * g.T * g.Cout;
+  float4 a = *reinterpret_cast<const float4*>(g.partial + row * g.Cout + n);
+  for (int sp = 1; sp < g.splits; ++sp) {
+    const float4 q = *reinterpret_cast<const float4*>(g.partial + sp * stride + row * g.Cout + n);
+    a.x += q.x; a.y += q.y; a.z += q.z; a.w += q.w;
+  }
+  float v[4] = {a.x, a.y, a.z, a.w};
+  if (g.bias) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+    v[0] += bv.x; v[1] += bv.y; v[2] += bv.z; v[3] += bv.w;
+  }
+  if (g.post_act != MTTS_ACT_NONE) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, 0.f);
+  }
+  float4 rv = make_float4(0.f, 0.f, 0.f, 0.f), ov = rv;
+  if (g.res) rv = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
+  if (g.accumulate) ov = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
+  v[0] = (v[0] + rv.x) * g.out_scale + ov.x;
+  v[1] = (v[1] + rv.y) * g.out_scale + ov.y;
+  v[2] = (v[2] + rv.z) * g.out_scale + ov.z;
+  v[3] = (v[3] + rv.w) * g.out_scale + ov.w;
+  if (g.y) *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n) = make_float4(v[0], v[1], v[2], v[3]);
+  if (g.op) {
+    if (g.op_act != MTTS_ACT_NONE) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.op_act, g.op_slope);
+    }
+    store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v);
   }
 }
 
@@ -454,7 +507,7 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "conv_tc", (long long)e);
     attr = true;
   }
-  const int64_t tiles = (int64_t)a.B * cdiv64(a.T, PAIR ? 256 : 128) * cdiv64(a.Cout, BN);
+  const int64_t tiles = (int64_t)a.B * cdiv64(a.T, PAIR ? 256 : 128) * cdiv64(a.Cout, BN) * a.splits;
   if (PAIR) {
     const int64_t pairs = tiles < g_ctc_sms / 2 ? tiles : g_ctc_sms / 2;
     cudaLaunchConfig_t cfg = {};
@@ -528,6 +581,33 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
       if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(g_ctc_sms * 4) / 5) break;
     }
   }
+  // split-K for dense layers with too few output tiles to fill the GPU (the early steps of the AR loops, the N = 1024
+  // layers up to ~30 steps): narrow tiles would pay the 55-cycle minimum per MMA (tools/microbench/mma_floor.cu) on
+  // every k-step, so K is split across CTAs at full tile width instead and a second kernel reduces the partials
+  int splits = 1;
+  {
+    const char* ke = getenv("MEGATTS2_TC_SPLITK");
+    const int64_t rows = (int64_t)p.B * p.Tout;
+    const int64_t t128 = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, 128);
+    const int nk = (p.Cin + 63) / 64;
+    if (!(ke && ke[0] == '0') && SWB == 128 && p.k == 1 && p.out_shift == 0 && p.tc_partial && p.Cout >= 128 &&
+        t128 < (int64_t)(g_ctc_sms * 4) / 5) {
+      int sk = (int)(g_ctc_sms / t128);
+      const char* me = getenv("MEGATTS2_TC_SPLITK_MAX");
+      const char* ge = getenv("MEGATTS2_TC_SPLITK_MARGIN");
+      const int sk_max = me ? atoi(me) : 8;
+      const double margin = ge ? atof(ge) : 0.85;
+      if (sk > sk_max) sk = sk_max;
+      if (sk > nk / 2) sk = nk / 2;
+      if (sk >= 2 && (int64_t)sk * rows * p.Cout * 4 <= p.tc_partial_bytes) {
+        const int64_t tiles_bn = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, BN);
+        const double waves = (double)cdiv64(tiles_bn, g_ctc_sms);
+        const double cost_now = waves * nk * 24.0 * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
+        const double cost_split = (double)cdiv64(nk, sk) * 24.0 * 65.0 + 9000.0;             // + reduction kernel
+        if (cost_split < margin * cost_now) { splits = sk; BN = 128; }
+      }
+    }
+  }
   // CTA pairs (cta_group::2): two SMs share one 256 x 128 tile; each stages its own 128 activation rows and HALF of the
   // weight tile, so a quarter fewer bytes cross L2 -> SM and a quarter fewer operand bytes are read from shared memory
   // per FLOP.  Measured (tools/bench_tc_shapes.py): +1..3 % on the dense layers, -5 % on the ragged-T convolutions
@@ -538,7 +618,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   const char* se = getenv("MEGATTS2_TC_SWB64");
   if (se && se[0] == '1') SWB = 64;
   bool pair = false;
-  if (pair_mode && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || pair_mode >= 3)) {
+  if (pair_mode && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || pair_mode >= 3)) {
     const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
     pair = t256 >= (int64_t)(g_ctc_sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
@@ -559,6 +639,14 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.out_shift = p.out_shift; a.ybe = p.y_batch_elems ? p.y_batch_elems : (int64_t)p.Tout * p.ldy;
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
+  a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
+  if (splits > 1) {
+    MTTS_TRY((conv_tc_launch<128, 128>(maps, a, st)));
+    const int64_t total4 = (int64_t)p.B * p.Tout * p.Cout / 4;
+    tc_splitk_reduce_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(a, total4);
+    MTTS_CHECK_LAUNCH();
+    return 0;
+  }
   if (pair) return SWB == 128 ? conv_tc_launch<128, 128, 1>(maps, a, st) : conv_tc_launch<128, 64, 1>(maps, a, st);
   if (SWB == 64 && BN == 128) return conv_tc_launch<128, 64>(maps, a, st);
   if (SWB == 64 && BN == 64) return conv_tc_launch<64, 64>(maps, a, st);

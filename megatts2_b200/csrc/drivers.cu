@@ -43,21 +43,34 @@ static inline int64_t conv_tc_scratch_need(int64_t B, int64_t Tp, int64_t C) { r
 // (cached) TMA descriptors keep hitting across the steps of an autoregressive loop
 struct TcScratch { void* p; int64_t bytes; int64_t rows_cap; };
 
+constexpr int64_t TC_PARTIAL_BYTES = 64ll << 20;
+static inline int64_t tc_planes_bytes(const mtts_encoder* e, int64_t rows_cap) {
+  return align_up(6 * rows_cap * ((int64_t)e->d_model + e->ff_dim) + 8192, 1024);
+}
 static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
   if (e->engine != 1) return 0;
   const int kmax = e->ff_dim > e->d_model ? e->ff_dim : e->d_model;
   // conv-FF (k = 5): padded planes need 4 halo rows per sequence; rows_cap + 4*rows_cap covers any batch split
   if (e->conv_ff) return linear_tc_scratch_bytes(5 * rows_cap + 64, kmax) + 4096;
-  // linear FF, fused plane flow: P_a (rows_cap x D) and P_b (rows_cap x F), three bf16 planes each
-  return 6 * rows_cap * ((int64_t)e->d_model + e->ff_dim) + 8192;
+  // linear FF, fused plane flow: P_a (rows_cap x D) and P_b (rows_cap x F), three bf16 planes each,
+  // followed by the split-K partial-sum area (used when a layer has too few tiles to fill the GPU)
+  return tc_planes_bytes(e, rows_cap) + TC_PARTIAL_BYTES;
+}
+static inline void tc_partial_area(const mtts_encoder* e, const TcScratch* tc, void** ptr, int64_t* bytes) {
+  *ptr = nullptr; *bytes = 0;
+  if (!tc || !tc->p || e->conv_ff) return;
+  const int64_t off = tc_planes_bytes(e, tc->rows_cap);
+  if (tc->bytes >= off + TC_PARTIAL_BYTES) { *ptr = (char*)tc->p + off; *bytes = TC_PARTIAL_BYTES; }
 }
 
 // tensor-core GEMM on planes that a producer kernel already wrote (no split pass); optional plane output
 static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int K, int N, const void* wtc,
                       const float* bias, const float* res, int ldr, float* y, int ldy, int post_act,
-                      __nv_bfloat16* out_planes, int out_ld, cudaStream_t st) {
+                      __nv_bfloat16* out_planes, int out_ld, cudaStream_t st, void* partial = nullptr,
+                      int64_t partial_bytes = 0) {
   mtts_conv_params p = linear_params(nullptr, K, nullptr, bias, y, ldy, M, K, N);
   p.res = res; p.ldr = ldr; p.post_act = post_act;
+  p.tc_partial = partial; p.tc_partial_bytes = partial_bytes;
   p.w_tc = wtc; p.tc_scratch = planes; p.tc_scratch_bytes = 6 * tc->rows_cap * (int64_t)K + 4096; p.tc_rows_cap = tc->rows_cap;
   p.tc_presplit = 1;
   if (out_planes) {
@@ -123,7 +136,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
   // Fused plane flow (tensor-core engine, linear FF, M >= 128): LayerNorm / attention / the FF1 epilogue write
   // their result directly as bf16x3 planes, so no split pass and no fp32 round trip feeds the GEMMs.
   bool fused = e->engine == 1 && !e->conv_ff && tc && tc->p && M >= 128 && D % 32 == 0 && F % 32 == 0 &&
-               tc->bytes >= 6 * tc->rows_cap * ((int64_t)D + F) + 8192 && tc->rows_cap >= M;
+               tc->bytes >= tc_planes_bytes(e, tc->rows_cap) && tc->rows_cap >= M;
   for (int l = 0; fused && l < e->n_layers; ++l)
     fused = e->layers[l].w_qkv_tc && e->layers[l].w_o_tc && e->layers[l].w_ff1_tc && e->layers[l].w_ff2_tc;
   __nv_bfloat16* Pa = nullptr;
@@ -133,12 +146,15 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
     Pb = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)(Pa + 3 * tc->rows_cap * (int64_t)D)) + 1023) & ~(uintptr_t)1023);
   }
   const PlanesOut pa_out{Pa, tc ? tc->rows_cap * (int64_t)D : 0, D, MTTS_ACT_NONE, 0.f};
+  void* part = nullptr;
+  int64_t part_bytes = 0;
+  if (fused) tc_partial_area(e, tc, &part, &part_bytes);
   for (int l = 0; l < e->n_layers; ++l) {
     const mtts_encoder_layer& L = e->layers[l];
     const bool last = last_row_only && (l == e->n_layers - 1);
     if (fused) {
       MTTS_TRY(layernorm_ex(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
-      MTTS_TRY(lin_planes(tc, Pa, M, D, 3 * D, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, nullptr, 0, st));
+      MTTS_TRY(lin_planes(tc, Pa, M, D, 3 * D, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, nullptr, 0, st, part, part_bytes));
     } else {
       // h = LN1(x);  qkv = h Wqkv + b
       MTTS_TRY(layernorm(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, h, D, M, D, 1e-5f, 0, 0, st));
@@ -155,11 +171,11 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       if (fused) {
         ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D;
         MTTS_TRY(attention(ap, st));
-        MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st));
+        MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st, part, part_bytes));
         MTTS_TRY(layernorm_ex(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
         // FF1: relu(h W1 + b1) goes straight to planes P_b; FF2 reads them
-        MTTS_TRY(lin_planes(tc, Pa, M, D, F, L.w_ff1_tc, L.b_ff1, nullptr, 0, nullptr, 0, MTTS_ACT_RELU, Pb, F, st));
-        MTTS_TRY(lin_planes(tc, Pb, M, F, D, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, nullptr, 0, st));
+        MTTS_TRY(lin_planes(tc, Pa, M, D, F, L.w_ff1_tc, L.b_ff1, nullptr, 0, nullptr, 0, MTTS_ACT_RELU, Pb, F, st, part, part_bytes));
+        MTTS_TRY(lin_planes(tc, Pb, M, F, D, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, nullptr, 0, st, part, part_bytes));
         xin = xw;
         continue;
       }

@@ -83,14 +83,18 @@ def test_plm_tc_engine_matches_golden_ids(golden, weights_cpu):
 def test_encoder_tc_vs_ffma(weights_cpu):
     from megatts2_b200.modules.transformer import run_encoder
     plm = helpers.build_plm(weights_cpu("plm"), DEV)
-    x = torch.randn(8, 40, 1024, generator=gen(3)).to(DEV)
-    plm.plm.engine = 0
-    y0 = plm.plm(x)
-    plm.plm.engine = 1
-    y1 = plm.plm(x)
-    assert (y0 - y1).abs().max().item() < 5e-4
-    l1 = run_encoder(plm.plm, list(plm.plm.layers), x, last_row_only=True)
-    assert (l1[:, 0] - y0[:, -1]).abs().max().item() < 5e-4
+    # (8, 40): every dense layer is under-filled -> split-K at full tile width; (16, 64): only the N = 1024 layers;
+    # (64, 40): full grids (CTA pairs); (5, 33): ragged rows
+    for i, (B, T) in enumerate([(8, 40), (16, 64), (64, 40), (5, 33)]):
+        x = torch.randn(B, T, 1024, generator=gen(3 + i)).to(DEV)
+        plm.plm.engine = 0
+        y0 = plm.plm(x)
+        plm.plm.engine = 1
+        y1 = plm.plm(x)
+        assert (y0 - y1).abs().max().item() < 5e-4, (B, T)
+        assert torch.equal(y1, plm.plm(x)), "the split-K reduction order is fixed: bit-reproducible"
+        l1 = run_encoder(plm.plm, list(plm.plm.layers), x, last_row_only=True)
+        assert (l1[:, 0] - y0[:, -1]).abs().max().item() < 5e-4, (B, T)
 
 
 # ------------------------------------------------------------------ tensor-core convolution engine
