@@ -13,6 +13,10 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box via gpurun)")
+    # The CPU oracle legs: torch's default of one thread per host CPU (128 on the GPU box) oversubscribes the small
+    # GEMMs of the checker and made the GPU suite take 12 min instead of 6 (bench.py calibrates the same way and
+    # lands on 32).  The cap changes nothing about the results.
+    torch.set_num_threads(max(1, min(32, os.cpu_count() or 1)))
 
 
 def pytest_collection_modifyitems(config, items):

@@ -13,7 +13,6 @@ from oracle import weights
 
 from conftest import GOLDEN
 
-torch.set_num_threads(max(1, os.cpu_count() or 1))
 
 
 def test_state_dict_keys_match_reference():
