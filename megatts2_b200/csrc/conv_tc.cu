@@ -1,13 +1,18 @@
-// Tensor-core tap-GEMM: stride-1 Conv1d (any kernel size / dilation / padding mode) on tcgen05 with
-// the bf16x3 split of gemm_tc.cu.  Used for the HiFi-GAN ResBlock convs and the ConvBlock stacks
-// (modules/convnet.py:13-18; speechbrain HifiGAN ResBlock1), i.e. wherever Cin % 8 == 0, Cin >= 32 and
-// Cout in {32, 64, >= 128}.
+// Tensor-core tap-GEMM: every stride-1 Conv1d / ConvTranspose1d (2-tap form) / Linear (k = 1) on tcgen05 with fp32-grade
+// accuracy: both operands are split into three bf16 planes (x = x1 + x2 + x3 to 2^-24) and the six products whose
+// weight is >= 2^-16 are issued as bf16 MMAs into two TMEM accumulators (x1*w1 | the five corrections).
+// Eligible wherever Cin % 8 == 0, Cin >= 32, Cout in {32, 64, >= 128 and % 32 == 0} and B*T >= 128; everything else
+// stays on the exact FFMA engine (tapconv.cu).  Reference layers: modules/convnet.py:13-18, modules/transformer.py:16-102,
+// the speechbrain HiFi-GAN generator (ResBlock1 convs, ConvTranspose1d upsamplers).
 //
-// Data flow:  fp32 activations (B,T,C) --split_pad--> three bf16 planes (B, T + halo, C) with the
-// padding MATERIALISED (zero / reflect / replicate) and the pre-activation applied, so that the conv
-// becomes a "valid" conv over the planes and tap j of an output tile is simply the same 128-row
-// tile shifted by j*dil rows: one 3-D TMA box load per (tap, channel slab), no im2col, the k-fold
-// re-reads are served by L2.  Weights are packed per tap as (k, Cout, Cin) bf16 planes (K-major B).
+// Data flow:  activation planes (B, T + halo, C) bf16 x 3 with the padding MATERIALISED (zero / reflect / replicate)
+// and the pre-activation applied - written by the producing kernel (LayerNorm, attention, the previous tap-GEMM's
+// epilogue) or, failing that, by split_pad_bf16x3_kernel - so that the conv is a "valid" conv over the planes and tap j
+// of an output tile is simply the same 128-row tile shifted by j*dil rows: one 3-D TMA box load per (tap, channel
+// slab, plane), no im2col, the k-fold re-reads are served by L2.  Weights are packed per tap as (k, Cout, Cin) bf16
+// planes (K-major B).  Variants: tile width BN 128 / 64 / 32 by grid fill, CTA pairs (cta_group::2) for the dense
+// layers, split-K with a fixed-order reduction kernel for under-filled dense layers.  DESIGN.md section 4 has the
+// anatomy and the measured bounds.
 #include <mutex>
 #include <unordered_map>
 
