@@ -186,3 +186,39 @@ def test_compute_num_frames_matches_both_lhotse_forms():
         form_a = int(Decimal(round(duration / (hop / sr), ndigits=8)).quantize(0, rounding=ROUND_HALF_UP))
         form_b = (n + hop // 2) // hop
         assert compute_num_frames(n) == form_a == form_b, n
+
+
+def test_ctypes_structs_match_the_c_header(tmp_path):
+    """The ctypes mirrors in megatts2_b200/_lib.py must have the size AND field offsets of the structs in
+    include/megatts2_b200.h: a plain-C probe (gcc, no CUDA) prints sizeof / offsetof for every field."""
+    import ctypes as C
+    import re
+    import shutil
+    import subprocess
+    from conftest import ROOT
+    from megatts2_b200 import _lib as L
+    if shutil.which("gcc") is None:
+        pytest.skip("no gcc")
+    pairs = {"mtts_conv_params": L.ConvParams, "mtts_attn_params": L.AttnParams, "mtts_encoder_layer": L.EncoderLayer,
+             "mtts_encoder": L.Encoder, "mtts_plm": L.PLM, "mtts_adm": L.ADM, "mtts_conv_block": L.ConvBlock,
+             "mtts_convnet": L.ConvNet, "mtts_convnet_double": L.ConvNetDouble, "mtts_hifigan_resblock": L.HifiganResblock,
+             "mtts_hifigan": L.Hifigan}
+    lines = ["#include <stdio.h>", "#include <stddef.h>", '#include "megatts2_b200.h"', "int main(void) {"]
+    for cname, cls in pairs.items():
+        lines.append(f'  printf("{cname} sizeof %zu\\n", sizeof({cname}));')
+        for fname, _ in cls._fields_:
+            lines.append(f'  printf("{cname} {fname} %zu\\n", offsetof({cname}, {fname}));')
+    lines += ["  return 0;", "}"]
+    src = tmp_path / "probe.c"
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "probe"
+    subprocess.run(["gcc", "-std=c11", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    got = {}
+    for ln in out.splitlines():
+        m = re.match(r"(\w+) (\w+) (\d+)", ln)
+        got[(m.group(1), m.group(2))] = int(m.group(3))
+    for cname, cls in pairs.items():
+        assert got[(cname, "sizeof")] == C.sizeof(cls), cname
+        for fname, _ in cls._fields_:
+            assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
