@@ -222,3 +222,46 @@ def test_ctypes_structs_match_the_c_header(tmp_path):
         assert got[(cname, "sizeof")] == C.sizeof(cls), cname
         for fname, _ in cls._fields_:
             assert got[(cname, fname)] == getattr(cls, fname).offset, (cname, fname)
+
+
+def test_bf16x3_weight_planes_are_fp32_exact():
+    """pack_tc_planes: w1 + w2 + w3 reproduces the fp32 weight to 2^-24 relative (three bf16 mantissas cover fp32's 24
+    bits); this is what lets six bf16 MMAs stand in for one fp32 product.  Also the per-tap layout of the conv form."""
+    from megatts2_b200 import pack
+    g = torch.Generator().manual_seed(5)
+    w = torch.randn(96, 160, generator=g) * torch.logspace(-6, 3, 160)          # wide dynamic range
+    planes = pack.pack_tc_planes(w)
+    assert planes.shape == (3, 96, 160) and planes.dtype == torch.bfloat16
+    back = planes[0].double() + planes[1].double() + planes[2].double()
+    rel = ((back - w.double()).abs() / w.double().abs().clamp_min(1e-30)).max().item()
+    assert rel <= 2.0 ** -23, rel
+    assert (planes[1].float().abs() <= planes[0].float().abs() * 2.0 ** -7 + 1e-38).all()     # each plane ~2^-8 of the last
+    wc = torch.randn(8, 16, 5, generator=g)
+    pc = pack.pack_conv_tc_planes(wc)                                                          # (3, k, Cout, Cin)
+    assert pc.shape == (3, 5, 8, 16)
+    assert torch.equal(pc[0, 2], wc[:, :, 2].to(torch.bfloat16))
+
+
+def test_shard_bounds_properties_hypothesis():
+    hyp = pytest.importorskip("hypothesis")
+    from hypothesis import given, settings, strategies as st
+    from megatts2_b200.sharding import balance_by_cost, my_shard, shard_bounds
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(0, 5000), st.integers(1, 64))
+    def check(n, world):
+        b = shard_bounds(n, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == n
+        assert all(b[i][1] == b[i + 1][0] for i in range(world - 1))                  # contiguous, no gap / overlap
+        sizes = [hi - lo for lo, hi in b]
+        assert max(sizes) - min(sizes) <= 1                                            # balanced
+        assert all(my_shard(n, r, world) == b[r] for r in range(world))
+    check()
+
+    @settings(max_examples=100, deadline=None)
+    @given(st.lists(st.floats(0.0, 1e6, allow_nan=False), min_size=0, max_size=200), st.integers(1, 16))
+    def check_cost(costs, world):
+        parts = balance_by_cost(costs, world)
+        flat = sorted(i for p in parts for i in p)
+        assert len(parts) == world and flat == list(range(len(costs)))               # a partition of the items
+    check_cost()
