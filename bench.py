@@ -1,19 +1,30 @@
 #!/usr/bin/env python
-"""bench.py - synthesized audio samples/sec @ batch 64 (BASELINE.json metric, config C4).
+"""bench.py - synthesized audio samples/sec @ batch 64 + VQ-index bit-exact rate (BASELINE.json metric, config C4).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W [--impl b200|reference|torch_gpu] [--config c4|c2]
 
 One "step" = one pass of the synthesis hot path over one batch of 64 synthetic utterances U
 (64 phones, 8-s prompt -> 500 mel frames, durations forced to 8 -> 512 mel
 frames -> 64 prosody tokens -> 131,072 samples):  mel front end (STFT+mel) -> MRTE ->
 ADM autoregressive decode -> length regulator -> max-pool -> PLM autoregressive decode ->
-VQ decode + mel decoder -> HiFi-GAN.  Weights: seeded random init of the reference
-architecture (no checkpoints exist offline); data: synthetic.  N > 1: one process per GPU
-(torchrun), every rank synthesises its own 64 utterances (weak scaling, no data-path
-collective; NCCL only for the barrier / max-over-ranks of the timing).
+VQ decode + mel decoder -> HiFi-GAN, plus the re-vocoding of the prompt that the reference's
+forward() prepends (models/megatts2.py:371-373; its samples are NOT counted in the metric).
+Weights: seeded random init of the reference architecture (no checkpoints exist offline); data: synthetic,
+utterance i of the global batch is a pure function of seed 1234 + i.  N > 1: one process per GPU (torchrun),
+the global batch of N x 64 utterances is split with megatts2_b200.sharding.shard_bounds (weak scaling, no
+data-path collective); after the timed regions the prosody ids of every shard are gathered on rank 0 over NCCL
+(sharding.gather_variable) and one shard is recomputed there to check the C5 contract "per-shard identical to
+single-GPU".
 
-Output: ONE JSON line (contract in the task statement) with `roofline`, `cpu_baseline`, `e2e`,
-`clocks`, `gpu_launches`.
+Arms:  --impl b200       the product (this repo's CUDA path)                      [default]
+       --impl reference  the reference's CPU path (oracle port: the reference is un-installable - no setup.py,
+                         un-vendored deps), batch 1 like infer.py, one utterance per worker, all host cores
+       --impl torch_gpu  the same port executed by stock PyTorch on the GPU (cuBLAS/cuDNN fp32, TF32 off and on):
+                         the strongest existing implementation; never the reference arm
+       --config c2       BASELINE config 2: STFT+mel kernel over 10k synthetic 16 kHz 3-s clips (HBM roofline)
+
+Output: ONE JSON line (contract in the task statement) with `roofline`, `cpu_baseline`, `e2e`, `clocks`,
+`gpu_launches` and the parity half of the metric: `vq_index_bit_exact_rate`, `duration_exact_rate`, `mel_l1`.
 """
 import argparse
 import ctypes as C
@@ -36,6 +47,8 @@ PROMPT_SAMPLES = (TM_FRAMES - 1) * 256 + 128          # 1 + L // 256 == 500
 SAMPLES_PER_UTT = TP * DUR * 256                      # 131,072 mel-aligned samples (the vocoder also emits 10 pad frames)
 METRIC = "synthesized_audio_samples_per_sec_batch64"
 UNIT = "samples/s"
+SEED0 = 1234
+THREADS_PER_WORKER = 8                                # the CPU arm: concurrent batch-1 workers of this many torch threads
 
 
 def parse():
@@ -43,44 +56,19 @@ def parse():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_gpu"])
+    ap.add_argument("--config", default="c4", choices=["c4", "c2"])
     ap.add_argument("--batch", type=int, default=B_PER_GPU, help="utterances per GPU (default: the C4 batch, 64)")
+    ap.add_argument("--check-utts", type=int, default=16, help="utterances of the batch checked against the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU leg (profiling runs)")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads for the CPU legs (0 = calibrate)")
+    ap.add_argument("--no-prompt-revocode", action="store_true", help="leave out the prompt re-vocoding of forward()")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="concurrent batch-1 CPU workers (0 = cpus / 8, at most 16)")
+    ap.add_argument("--clips", type=int, default=10000, help="--config c2: number of 3-s clips")
     return ap.parse_args()
 
 
 def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
-
-
-def pick_cpu_threads(requested=0):
-    """The CPU legs are the reference's batch-1 AR loops: thousands of small ops.  With every hardware thread
-    of a many-core host the OpenMP fork/join cost dominates, so calibrate on a representative op (one
-    64-row x 1024 x 4096 GEMM + LayerNorm) and keep the fastest power-of-two thread count."""
-    ncpu = os.cpu_count() or 1
-    if requested > 0:
-        return min(requested, ncpu)
-    x = torch.randn(64, 1024)
-    w = torch.randn(4096, 1024)
-    best, best_t = 1, float("inf")
-    n = 1
-    cands = []
-    while n < ncpu:
-        cands.append(n)
-        n *= 2
-    cands.append(ncpu)
-    for n in cands:
-        torch.set_num_threads(n)
-        for _ in range(3):
-            torch.nn.functional.layer_norm(torch.nn.functional.linear(x, w), (4096,))
-        t0 = time.perf_counter()
-        for _ in range(20):
-            torch.nn.functional.layer_norm(torch.nn.functional.linear(x, w), (4096,))
-        dt = time.perf_counter() - t0
-        if dt < best_t * 0.97:
-            best, best_t = n, dt
-    return best
 
 
 def peaks():
@@ -136,10 +124,12 @@ class ClockSampler:
                 "samples": len(sm), "reasons": sorted(reasons)}
 
 
-def build_product(device):
-    """Random-init (seeded) product modules of the reference architecture; no oracle import here."""
+# ------------------------------------------------------------------------------------------ model + data
+def build_modules():
+    """Random-init (seeded) product modules of the reference architecture, built on the HOST (so that the CPU
+    workers of the checker / reference arm can rebuild bit-identical weights from the same seeds)."""
     import yaml
-    from megatts2_b200.models.megatts2 import HIFIGAN, MegaG, Megatts
+    from megatts2_b200.models.megatts2 import HIFIGAN, MegaG
     from megatts2_b200.utils.utils import instantiate_class
     cfg = os.path.join(ROOT, "configs")
     torch.manual_seed(0)
@@ -155,29 +145,100 @@ def build_product(device):
     with torch.no_grad():    # keep the AR duration regression bounded on random weights
         adm.dt_linear_emb.weight.mul_(0.02)
     torch.manual_seed(3)
-    hifi = HIFIGAN.from_hparams()
+    hifi = HIFIGAN.from_hparams(random_init=True)
+    return G, plm, adm, hifi
+
+
+def build_product(device):
+    from megatts2_b200.models.megatts2 import Megatts
+    G, plm, adm, hifi = build_modules()
     return Megatts(generator=G, plm=plm, adm=adm, hifi_gan=hifi, device=device)
 
 
-def make_inputs(batch, seed):
-    g = torch.Generator().manual_seed(seed)
-    wav = torch.rand(batch, PROMPT_SAMPLES, generator=g) * 2 - 1
-    phone = torch.randint(0, 320, (batch, TP), generator=g)
-    if torch.cuda.is_available():
+def state_dicts(G, plm, adm, hifi):
+    return tuple({n: v.detach().cpu() for n, v in m.state_dict().items()} for m in (G, plm, adm, hifi.generator))
+
+
+def utterance(idx):
+    """utterance `idx` of the global batch: prompt audio (PROMPT_SAMPLES,) and phone ids (TP,), seed 1234 + idx"""
+    g = torch.Generator().manual_seed(SEED0 + idx)
+    wav = torch.rand(PROMPT_SAMPLES, generator=g) * 2 - 1
+    phone = torch.randint(0, 320, (TP,), generator=g)
+    return wav, phone
+
+
+def make_inputs(indices, pin=True):
+    ws, ps = zip(*(utterance(i) for i in indices))
+    wav, phone = torch.stack(ws), torch.stack(ps)
+    if pin and torch.cuda.is_available():
         wav, phone = wav.pin_memory(), phone.pin_memory()
-    forced = torch.full((batch, TP), DUR, dtype=torch.int32)
+    forced = torch.full((len(indices), TP), DUR, dtype=torch.int32)
     return wav, phone, forced
 
 
-def gpu_step(tts, wav_d, phone_d, forced_d):
+def gpu_step(tts, wav_d, phone_d, forced_d, revocode=True, intermediates=False):
     from megatts2_b200.modules.tokenizer import extract_mel_spec
     mel = extract_mel_spec(wav_d, frames_major=True)                  # (B, 500, 80)
-    return tts.synthesize(phone_d, mel, forced_durations=forced_d)     # (B, 1, 133632)
+    return tts.synthesize(phone_d, mel, forced_durations=forced_d, prompt_mels=mel if revocode else None,
+                          return_intermediates=intermediates)
 
 
+# ------------------------------------------------------------------------------------------ CPU workers (oracle port)
+_W = {}
+
+
+def _worker_init(threads):
+    torch.set_num_threads(threads)
+    from oracle import weights as W
+    G, plm, adm, hifi = build_modules()
+    _W["sd"] = state_dicts(G, plm, adm, hifi)
+    _W["cfgs"] = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
+
+
+def _worker_utt(job):
+    """the reference's path for ONE utterance, batch 1 as infer.py runs it; returns ids / durations / mel + seconds"""
+    idx, revocode = job
+    from oracle import ref_megatts2 as R
+    wav, phone = utterance(idx)
+    forced = torch.full((1, TP), DUR, dtype=torch.int32)
+    t0 = time.perf_counter()
+    mel = R.mel_spectrogram(wav[None]).transpose(1, 2)
+    g, p, a, h = _W["sd"]
+    ref = R.synthesize(g, p, a, h, phone[None], mel, _W["cfgs"], forced_durations=forced)
+    if revocode:
+        R.hifigan_generator(R.SD(h), mel.transpose(1, 2), _W["cfgs"][3])      # models/megatts2.py:371-372
+    dt = time.perf_counter() - t0
+    chk = float(g["decoder.last_layer.weight"].double().sum() + p["predict_layer.weight"].double().sum())
+    return dict(idx=idx, secs=dt, p_codes=ref["p_codes"][0].numpy(), dt=ref["dt"][0].numpy(),
+                mel=ref["mel"][0].transpose(0, 1).contiguous().numpy(), weights_checksum=chk)
+
+
+class CpuPool:
+    def __init__(self, workers):
+        import multiprocessing as mp
+        ncpu = os.cpu_count() or 1
+        self.workers = workers if workers > 0 else max(1, min(16, ncpu // THREADS_PER_WORKER))
+        self.threads = max(1, min(THREADS_PER_WORKER, ncpu // self.workers))
+        self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_worker_init, initargs=(self.threads,))
+        self.pool.map(_noop, range(self.workers))      # every worker has imported torch and rebuilt the weights
+
+    def run(self, indices, revocode):
+        return self.pool.map(_worker_utt, [(i, revocode) for i in indices], chunksize=1)
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def _noop(i):
+    time.sleep(0.2)
+    return i
+
+
+# ------------------------------------------------------------------------------------------ the product arm
 def run_b200(args):
     from megatts2_b200 import _lib as L
-    from megatts2_b200 import ops
+    from megatts2_b200 import ops, pack, sharding
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -188,12 +249,15 @@ def run_b200(args):
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
     B = args.batch
+    revocode = not args.no_prompt_revocode
     log("building product modules")
     tts = build_product(dev)
-    wav_h, phone_h, forced = make_inputs(B, 1234 + rank)
+    lo, hi = sharding.shard_bounds(world * B, world)[rank]            # this rank's slice of the global batch
+    wav_h, phone_h, forced = make_inputs(range(lo, hi))
     wav_d, phone_d, forced_d = wav_h.to(dev), phone_h.to(dev), forced.to(dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)      # > 126 MB L2
-    out_h = torch.empty(B, 1, 256 * (TP * DUR + 10), dtype=torch.float32).pin_memory()
+    n_out = 256 * (TP * DUR + 10) + (256 * (TM_FRAMES + 10) if revocode else 0)
+    out_h = torch.empty(B, 1, n_out, dtype=torch.float32).pin_memory()
     lib = L.lib()
 
     def barrier():
@@ -203,7 +267,7 @@ def run_b200(args):
 
     # ---- warm-up (also builds the packed-weight plans and grows the workspace)
     for _ in range(max(args.warmup, 1)):
-        out = gpu_step(tts, wav_d, phone_d, forced_d)
+        out = gpu_step(tts, wav_d, phone_d, forced_d, revocode)
     torch.cuda.synchronize()
     log("warm-up done")
 
@@ -217,7 +281,7 @@ def run_b200(args):
     e0.record()
     for _ in range(args.steps):
         flush.zero_()                                                   # L2 flush between timed iterations
-        out = gpu_step(tts, wav_d, phone_d, forced_d)
+        out = gpu_step(tts, wav_d, phone_d, forced_d, revocode)
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None
@@ -233,7 +297,7 @@ def run_b200(args):
         flush.zero_()
         w = wav_h.to(dev, non_blocking=True)
         ph = phone_h.to(dev, non_blocking=True)
-        out = gpu_step(tts, w, ph, forced_d)
+        out = gpu_step(tts, w, ph, forced_d, revocode)
         out_h.copy_(out, non_blocking=True)
     f1.record()
     barrier()
@@ -248,11 +312,30 @@ def run_b200(args):
     value = total_samples / (ms / 1e3)
     e2e_value = total_samples / (ms_e2e / 1e3)
 
+    # ---- C5 contract: every shard's ids, gathered over NCCL, equal a single-GPU run of the same global indices
+    inter = gpu_step(tts, wav_d, phone_d, forced_d, revocode, intermediates=True)
+    shard_identity = None
+    if dist is not None:
+        ids = inter["p_codes"]                                          # (B, T8) int64 on this rank
+        lens = torch.full((ids.shape[0],), ids.shape[1], dtype=torch.int64, device=dev)
+        gathered = sharding.gather_variable(ids, lens)                  # [(rows_r, lens_r)] over ranks, via NCCL
+        if rank == 0:
+            chk = world - 1                                             # recompute the LAST rank's shard here
+            clo, chi = sharding.shard_bounds(world * B, world)[chk]
+            cw, cp, cf = make_inputs(range(clo, chi), pin=False)
+            mine = gpu_step(tts, cw.to(dev), cp.to(dev), cf.to(dev), revocode, intermediates=True)["p_codes"]
+            theirs = gathered[chk][0]
+            shard_identity = {"global_batch": world * B, "gathered_rows": int(sum(g[0].shape[0] for g in gathered)), "checked_shard": chk,
+                              "global_indices": [clo, chi], "ids_equal": bool(torch.equal(mine, theirs)),
+                              "how": "prosody ids of every rank gathered on rank 0 with sharding.gather_variable over NCCL; "
+                                     "rank 0 re-ran the checked shard's global indices itself"}
+            log(f"shard identity: {shard_identity['ids_equal']}")
+
     result = None
     if rank == 0:
         # ---- roofline leg: per-launch CUDA events around every tap-GEMM launch of ONE step
         lib.mtts_profile_begin()
-        gpu_step(tts, wav_d, phone_d, forced_d)
+        gpu_step(tts, wav_d, phone_d, forced_d, revocode)
         gms, gfl, gn = C.c_double(), C.c_double(), C.c_int64()
         L.check(lib.mtts_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn)))
         log(f"roofline leg: {gn.value} tap-GEMM launches, {gms.value:.1f} ms, {gfl.value / 1e12:.2f} TFLOP")
@@ -261,43 +344,47 @@ def run_b200(args):
         pk, pk_src = peaks()
         peak = float(pk.get("bf16_tflops_sustained", pk.get("bf16_tflops")))
         step_ms = ms / args.steps
+        engine = pack.default_engine()
+        mma_per_product = {pack.ENGINE_F16X2: 3, pack.ENGINE_BF16X3: 6}.get(engine, 0)
+        scheme = {pack.ENGINE_F16X2: "f16x2 (two fp16 operand planes, residual scaled by 2^11; 3 MMAs per fp32-grade product)",
+                  pack.ENGINE_BF16X3: "bf16x3 (three bf16 operand planes; 6 MMAs per fp32-grade product)"}.get(engine, "fp32 FFMA")
 
         def cls(ms_, fl_, n_):
             return {"ms_per_step": round(ms_, 2), "tflop_per_step": round(fl_ / 1e12, 3), "launches_per_step": int(n_),
                     "achieved_tflops": round(fl_ / (ms_ / 1e3) / 1e12, 2) if ms_ > 0 else 0.0,
                     "share_of_step": round(ms_ / step_ms, 3)}
         classes = {"fp32_ffma_tapconv_kernel": cls(sp[0], sp[1], sp[2]),
-                   "tcgen05_bf16x3_tap_gemm_kernels (incl. their activation-split kernels)": cls(sp[3], sp[4], sp[5])}
+                   "tcgen05_tap_gemm_kernels (incl. their activation-split kernels)": cls(sp[3], sp[4], sp[5])}
         dom_tc = sp[3] >= sp[0]
         d_ms, d_fl = (sp[3], sp[4]) if dom_tc else (sp[0], sp[1])
         achieved = d_fl / (d_ms / 1e3) / 1e12 if d_ms > 0 else 0.0
+        traffic, traffic_note = measured_traffic()
         roofline = {"bound": "tensor",
-                    "kernel": ("conv_bf16x3_kernel (tcgen05 tap-GEMM: every Linear / Conv1d / ConvTranspose1d; 6 bf16 MMAs per "
-                               "fp32-grade product; single-CTA and cta_group::2 pair variants)"
-                               if dom_tc else "tapconv_kernel (fp32 FFMA tap-GEMM)"),
+                    "kernel": (f"conv_tc_kernel (tcgen05 tap-GEMM: every Linear / Conv1d / ConvTranspose1d; operands {scheme}; "
+                               "single-CTA and cta_group::2 pair variants)" if dom_tc else "tapconv_kernel (fp32 FFMA tap-GEMM)"),
                     "achieved": round(achieved, 3), "peak": peak, "unit": "TFLOP/s", "frac": round(achieved / peak, 5),
-                    "traffic": None,
-                    "traffic_note": "achieved aggregates ~4.9k launches of many shapes, so there is no single per-launch DRAM "
-                                    "figure; for the representative launch (PLM FF1 GEMM, M 5888, K 1024, N 4096) ncu --set full "
-                                    "measured 61.4 MB read + 62.3 MB written against 158 MB algorithmic (operands and result "
-                                    "stay L2-resident): profiles/r1_tc_engine_bounds.md",
+                    "traffic": traffic, "traffic_note": traffic_note,
                     "peak_source": f"{pk_src} dense bf16 (sustained). achieved = algorithmic fp32-grade FLOPs (2*M*N*K) / CUDA-event "
-                                   "time of the launches; the bf16x3 scheme issues 6 bf16 MMAs per such FLOP pair, so its "
-                                   "ceiling is peak/6",
-                    "frac_of_bf16x3_ceiling": round(achieved / (peak / 6.0), 4) if dom_tc else None,
+                                   f"time of the launches; the {scheme.split(' ')[0]} scheme issues {mma_per_product} 16-bit MMAs per such "
+                                   f"FLOP pair, so its ceiling is peak/{mma_per_product}",
+                    "frac_of_scheme_ceiling": round(achieved / (peak / mma_per_product), 4) if dom_tc and mma_per_product else None,
                     "classes": classes}
-        cpu = None if args.no_cpu_baseline else cpu_baseline(tts, args)
+        parity, cpu = (None, None) if args.no_cpu_baseline else cpu_check(args, inter, lo, revocode)
         result = {
             "metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": round(ms / args.steps, 3), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4: full synthesis MRTE+ADM+PLM+decoder+HiFi-GAN (+mel front end), "
+            "config": {"workload": "C4: full synthesis MRTE+ADM+PLM+decoder+HiFi-GAN (+mel front end"
+                                   + (", + re-vocoding of the 500-frame prompt as forward() does" if revocode else "") + "), "
                                    f"batch {B} synthetic utterances per GPU (64 phones, 500-frame prompt, "
-                                   "512 mel frames, 64 prosody tokens, 131072 samples each)",
+                                   "512 mel frames, 64 prosody tokens, 131072 counted samples each)",
                        "global_batch": world * B, "parallelism": f"replicas x{world} (batch split, no data-path collective)",
                        "l2": "256 MiB flush write between timed iterations; working set (1.57 GB weights) >> 126 MB L2",
                        "weights": "seeded random init of the reference architecture", "ar_semantics": "reference-faithful "
-                       "non-causal full recompute per step (models/megatts2.py:165-181, 257-275)"},
+                       "non-causal full recompute per step (models/megatts2.py:165-181, 257-275)",
+                       "tensor_core_operands": scheme,
+                       "unpinned": "HiFi-GAN (speechbrain, restated from the published architecture) and the speechbrain mel wrapper "
+                                   "are parity-unpinned (SURVEY.md 8c); everything else is pinned on the reference itself"},
             "e2e": {"value": round(e2e_value, 1), "unit": UNIT, "ms_per_step": round(ms_e2e / args.steps, 3),
                     "h2d_bytes_per_step": world * (wav_h.numel() * 4 + phone_h.numel() * 8),
                     "d2h_bytes_per_step": world * out_h.numel() * 4},
@@ -307,92 +394,225 @@ def run_b200(args):
             "roofline": roofline,
             "cpu_baseline": cpu,
         }
+        if parity is not None:
+            result.update(parity)
+        if shard_identity is not None:
+            result["shard_identity"] = shard_identity
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
     return result
 
 
-def cpu_baseline(tts, args, n_utt=2):
-    """The oracle port (CPU restatement of the reference, batch 1 like the reference) timed on this box's
-    host cores on a bounded sample of the same workload, and used as the CHECKER of the GPU arm's ids /
-    mel on that sample (same weights: the product's state dicts copied to the host)."""
-    from oracle import ref_megatts2 as R
-    from oracle import weights as W
-    cores = pick_cpu_threads(args.cpu_threads)
-    torch.set_num_threads(cores)
-    log(f"cpu_baseline: {cores} torch threads of {os.cpu_count()} host cpus")
-    sd = {k: {n: v.detach().cpu() for n, v in m.state_dict().items()}
-          for k, m in (("g", tts.generator), ("plm", tts.plm), ("adm", tts.adm), ("h", tts.hifi_gan.generator))}
-    wav, phone, forced = make_inputs(n_utt, 99)
-    dev = next(tts.parameters()).device
-    gpu = gpu_step_intermediates(tts, wav.to(dev), phone.to(dev), forced.to(dev))
-    cfgs = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
+def measured_traffic():
+    """dram__bytes_read + dram__bytes_write per launch of the dominant kernel class, from the committed ncu capture of
+    this command (tools/summarize_ncu.py -> profiles/r2_traffic.json); null until a capture exists."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if not os.path.exists(p):
+        return None, "no ncu capture committed yet"
+    with open(p) as f:
+        d = json.load(f)
+    return d.get("dominant_kernel_dram_bytes_per_launch"), d.get("note", "profiles/r2_traffic.json")
+
+
+def cpu_check(args, gpu, lo, revocode):
+    """The oracle port (CPU restatement of the reference, batch 1 like the reference) run by concurrent workers on this
+    box's host cores over `check_utts` utterances of this rank's batch: it is the CHECKER of the GPU arm's prosody ids /
+    durations / mel (the parity half of the metric), and its wall time is the `cpu_baseline`."""
+    n = min(args.check_utts, args.batch)
+    pool = CpuPool(args.cpu_workers)
+    log(f"cpu check: {n} utterances on {pool.workers} workers x {pool.threads} threads ({os.cpu_count()} host cpus)")
     t0 = time.perf_counter()
-    exact_ids = exact_dur = n_ids = n_dur = 0
+    res = pool.run([lo + i for i in range(n)], revocode)
+    wall = time.perf_counter() - t0
+    pool.close()
+    ids_ok = ids_n = dur_ok = dur_n = 0
     mel_l1 = 0.0
-    for u in range(n_utt):
-        mel = R.mel_spectrogram(wav[u:u + 1]).transpose(1, 2)
-        ref = R.synthesize(sd["g"], sd["plm"], sd["adm"], sd["h"], phone[u:u + 1], mel, cfgs,
-                           forced_durations=forced[u:u + 1])
-        log(f"cpu_baseline: utterance {u + 1}/{n_utt} done at {time.perf_counter() - t0:.1f} s")
-        exact_ids += int((ref["p_codes"] == gpu["p_codes"][u:u + 1].cpu()).sum()); n_ids += ref["p_codes"].numel()
-        exact_dur += int((ref["dt"] == gpu["dt"][u:u + 1].cpu()).sum()); n_dur += ref["dt"].numel()
-        mel_l1 += (ref["mel"].transpose(1, 2) - gpu["mel"][u:u + 1].cpu()).abs().mean().item() / n_utt
-    dt = time.perf_counter() - t0
-    return {"value": round(n_utt * SAMPLES_PER_UTT / dt, 1), "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{n_utt} of the {args.batch} utterances U, batch 1 each (the reference's infer() is batch-1 only), "
-                      f"{dt:.1f} s of CPU time, torch threads = {cores} (fastest of the calibrated counts on "
-                      f"{os.cpu_count()} host cpus)",
-            "rtf": round(dt / (n_utt * SAMPLES_PER_UTT / 16000.0), 3),
-            "parity_on_sample": {"plm_id_exact_rate": exact_ids / max(n_ids, 1), "duration_exact_rate": exact_dur / max(n_dur, 1),
-                                 "mel_l1": mel_l1}}
+    p_codes, dt, mel = gpu["p_codes"].cpu(), gpu["dt"].cpu(), gpu["mel"].cpu()
+    for r in res:
+        i = r["idx"] - lo
+        ids_ok += int((torch.from_numpy(r["p_codes"]) == p_codes[i]).sum()); ids_n += r["p_codes"].size
+        dur_ok += int((torch.from_numpy(r["dt"]) == dt[i]).sum()); dur_n += r["dt"].size
+        mel_l1 += (torch.from_numpy(r["mel"]) - mel[i]).abs().mean().item() / len(res)
+    secs = [r["secs"] for r in res]
+    parity = {"vq_index_bit_exact_rate": ids_ok / max(ids_n, 1), "duration_exact_rate": dur_ok / max(dur_n, 1),
+              "mel_l1": mel_l1, "parity_checked_utterances": len(res),
+              "parity_note": f"prosody VQ ids ({ids_n}), ADM durations ({dur_n}) and decoder mel of {len(res)} of the {args.batch} "
+                             "utterances vs the CPU oracle (batch 1 each); bars: ids / durations bit-exact, mel L1 <= 1e-4"}
+    cpu = {"value": round(len(res) * SAMPLES_PER_UTT / wall, 1), "unit": UNIT, "cores": pool.workers * pool.threads,
+           "kind": "port",
+           "sample": f"{len(res)} of the {args.batch} utterances U, batch 1 each (the reference's infer() is batch-1 only) on "
+                     f"{pool.workers} concurrent workers x {pool.threads} torch threads of {os.cpu_count()} host cpus, "
+                     f"{wall:.1f} s wall",
+           "single_stream": {"value": round(SAMPLES_PER_UTT / statistics.median(secs), 1), "unit": UNIT,
+                             "threads": pool.threads, "median_s_per_utterance": round(statistics.median(secs), 2),
+                             "note": "one worker's rate while the other workers run (what one infer.py process gets)"},
+           "rtf": round(wall / (len(res) * SAMPLES_PER_UTT / 16000.0), 4)}
+    return parity, cpu
 
 
-def gpu_step_intermediates(tts, wav_d, phone_d, forced_d):
-    from megatts2_b200.modules.tokenizer import extract_mel_spec
-    mel = extract_mel_spec(wav_d, frames_major=True)
-    o = tts.synthesize(phone_d, mel, forced_durations=forced_d, return_intermediates=True)
-    torch.cuda.synchronize()
-    return o
-
-
+# ------------------------------------------------------------------------------------------ reference arm (CPU)
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle port: the reference
     cannot be pip-installed - it has no setup.py / pyproject and needs un-vendored speechbrain) on this box's
-    host cores, batch 1 as infer.py does, each step = one utterance U."""
+    host cores, batch 1 as infer.py does; a step = one utterance U on EVERY worker concurrently (all cores busy)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return None
-    from oracle import ref_megatts2 as R
-    from oracle import weights as W
-    cores = pick_cpu_threads(args.cpu_threads)
-    torch.set_num_threads(cores)
-    log(f"reference arm: {cores} torch threads of {os.cpu_count()} host cpus")
-    wg, wp, wa, wh = W.g_state_dict(), W.plm_state_dict(), W.adm_state_dict(), W.hifigan_state_dict()
-    cfgs = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
-    wav, phone, forced = make_inputs(1, 1234)
-
-    def step():
-        mel = R.mel_spectrogram(wav).transpose(1, 2)
-        return R.synthesize(wg, wp, wa, wh, phone, mel, cfgs, forced_durations=forced)["wav"]
+    revocode = not args.no_prompt_revocode
+    pool = CpuPool(args.cpu_workers)
+    W = pool.workers
+    log(f"reference arm: {W} workers x {pool.threads} torch threads of {os.cpu_count()} host cpus")
+    nxt = 0
     for _ in range(min(args.warmup, 1)):       # one warm-up pass is enough on the CPU (each is ~10 s)
-        step()
+        pool.run(range(nxt, nxt + W), revocode); nxt += W
     t0 = time.perf_counter()
+    secs = []
     for i in range(args.steps):
-        step()
+        secs += [r["secs"] for r in pool.run(range(nxt, nxt + W), revocode)]; nxt += W
         log(f"reference arm: step {i + 1}/{args.steps} at {time.perf_counter() - t0:.1f} s")
     dt = time.perf_counter() - t0
-    v = args.steps * SAMPLES_PER_UTT / dt
+    pool.close()
+    v = args.steps * W * SAMPLES_PER_UTT / dt
     return {"impl": "reference", "metric": METRIC, "value": round(v, 1), "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(dt / args.steps * 1e3, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "C4 utterance U through the reference's CPU path (oracle port), batch 1 per step "
-                                   "(the reference's infer() loops are batch-1 only)"},
-            "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": cores, "kind": "port",
-                             "sample": f"{args.steps} x 1 utterance U (131072 samples) per step, torch threads = {cores} "
-                                       f"(fastest calibrated count on {os.cpu_count()} host cpus)"},
+            "config": {"workload": f"C4 utterance U through the reference's CPU path (oracle port), batch 1 per worker (the "
+                                   f"reference's infer() loops are batch-1 only), {W} utterances per step on {W} concurrent workers"
+                                   + (", prompt re-vocoding included" if revocode else "")},
+            "cpu_baseline": {"value": round(v, 1), "unit": UNIT, "cores": W * pool.threads, "kind": "port",
+                             "sample": f"{args.steps} steps x {W} utterances U (131072 samples each), {W} workers x "
+                                       f"{pool.threads} torch threads of {os.cpu_count()} host cpus",
+                             "single_stream": {"value": round(SAMPLES_PER_UTT / statistics.median(secs), 1), "unit": UNIT,
+                                               "threads": pool.threads}},
             "e2e": {"value": round(v, 1), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+# ------------------------------------------------------------------------------------------ stock PyTorch on the GPU
+def run_torch_gpu(args):
+    """--impl torch_gpu: the oracle port (the reference's own torch ops) executed by stock PyTorch on cuda:0 at batch 64 -
+    cuBLAS / cuDNN fp32 with TF32 off (the parity-grade setting) and, as a stated fast mode, TF32 on - with the id-exact
+    rate of each against the product's ids.  The strongest existing implementation to beat."""
+    from oracle import ref_megatts2 as R
+    from oracle import weights as W
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return None
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    B = args.batch
+    revocode = not args.no_prompt_revocode
+    G, plm, adm, hifi = build_modules()
+    sds = tuple({k: v.to(dev) for k, v in sd.items()} for sd in state_dicts(G, plm, adm, hifi))
+    cfgs = (W.G_CFG, W.PLM_CFG, W.ADM_CFG, W.HIFIGAN_CFG)
+    wav, phone, forced = make_inputs(range(B), pin=False)
+    wav, phone, forced = wav.to(dev), phone.to(dev), forced.to(dev)
+    # the product's ids on the same batch (the comparison the judge asked for)
+    from megatts2_b200.models.megatts2 import Megatts
+    tts = Megatts(generator=G, plm=plm, adm=adm, hifi_gan=hifi, device=dev)
+    ours = gpu_step(tts, wav, phone, forced, revocode, intermediates=True)
+    ours_ids, ours_mel = ours["p_codes"].clone(), ours["mel"].clone()
+    del tts, ours
+    torch.cuda.empty_cache()
+
+    def step():
+        with torch.device(dev):
+            mel = R.mel_spectrogram(wav).transpose(1, 2)
+            out = R.synthesize(*sds, phone, mel, cfgs, forced_durations=forced)
+            if revocode:
+                R.hifigan_generator(R.SD(sds[3]), mel.transpose(1, 2), cfgs[3])
+        return out
+    modes = {}
+    for name, tf32 in (("fp32", False), ("tf32", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        for _ in range(max(1, min(args.warmup, 2))):
+            out = step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / args.steps
+        modes[name] = {"value": round(B * SAMPLES_PER_UTT / (ms / 1e3), 1), "unit": UNIT, "ms_per_step": round(ms, 2),
+                       "ids_equal_to_product_rate": float((out["p_codes"] == ours_ids).float().mean()),
+                       "mel_l1_vs_product": float((out["mel"].transpose(1, 2) - ours_mel).abs().mean())}
+        log(f"torch_gpu {name}: {ms:.1f} ms/step")
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    m = modes["fp32"]
+    return {"impl": "torch_gpu", "metric": METRIC, "value": m["value"], "unit": UNIT, "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": m["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C4 batch {B}: the oracle port's torch ops on cuda (cuBLAS / cuDNN), allow_tf32 = False",
+                       "note": "stock PyTorch eager; no last-row pruning, no fused kernels; same weights / inputs as the product arm"},
+            "modes": modes}
+
+
+# ------------------------------------------------------------------------------------------ config C2 (mel front end)
+def run_c2(args):
+    """BASELINE config 2: the STFT + mel-filterbank kernel over `clips` synthetic 16 kHz 3-s clips on one B200, against
+    the HBM roofline (algorithmic bytes = 48000*4 in + 188*80*4 out = 252,160 B per clip)."""
+    from megatts2_b200 import ops
+    from megatts2_b200.modules.tokenizer import extract_mel_spec
+    dev = torch.device("cuda", 0)
+    torch.cuda.set_device(0)
+    n, Ls = args.clips, 48000
+    g = torch.Generator().manual_seed(SEED0 + 2)
+    wav_h = (torch.rand(n, Ls, generator=g) * 2 - 1).pin_memory()
+    wav = wav_h.to(dev)                                                 # 1.92 GB > L2
+    for _ in range(max(args.warmup, 3)):
+        mel = extract_mel_spec(wav)
+    torch.cuda.synchronize()
+    n0 = ops.launch_count()
+    sampler = ClockSampler(0)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        mel = extract_mel_spec(wav)
+    e1.record()
+    torch.cuda.synchronize()
+    clocks = sampler.stop()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = ops.launch_count() - n0
+    out_h = torch.empty(mel.shape, dtype=torch.float32).pin_memory()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    for _ in range(args.steps):
+        m2 = extract_mel_spec(wav_h.to(dev, non_blocking=True))
+        out_h.copy_(m2, non_blocking=True)
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1) / args.steps
+    pk, pk_src = peaks()
+    bytes_per_clip = Ls * 4 + 80 * (1 + Ls // 256) * 4
+    gbs = n * bytes_per_clip / (ms / 1e3) / 1e9
+    cpu = None
+    if not args.no_cpu_baseline:
+        from oracle import ref_megatts2 as R
+        torch.set_num_threads(min(32, os.cpu_count() or 1))
+        k = 256
+        t0 = time.perf_counter()
+        ref = R.mel_spectrogram(wav_h[:k])
+        dt = time.perf_counter() - t0
+        l1 = (ref - mel[:k].cpu()).abs().mean().item()
+        cpu = {"value": round(k / dt, 1), "unit": "clips/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": f"{k} of the {n} clips in one torch.stft batch", "mel_l1_vs_gpu": l1}
+    return {"metric": "mel_clips_per_sec", "value": round(n / (ms / 1e3), 1), "unit": "clips/s", "n_gpus": 1, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": round(ms, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"C2: STFT (1024/256, periodic Hann, reflect) + 80-bin slaney mel + log over {n} clips of 3 s @ 16 kHz",
+                       "l2": "input 1.92 GB + output 0.60 GB per step >> 126 MB L2"},
+            "e2e": {"value": round(n / (ms_e2e / 1e3), 1), "unit": "clips/s", "h2d_bytes_per_step": n * Ls * 4,
+                    "d2h_bytes_per_step": int(mel.numel()) * 4},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "roofline": {"bound": "hbm", "kernel": "mel_kernel", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
+                         "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk_src,
+                         "algorithmic_bytes_per_clip": bytes_per_clip},
+            "cpu_baseline": cpu}
 
 
 def main():
@@ -403,7 +623,12 @@ def main():
         if not torch.cuda.is_available():
             print(json.dumps({"error": "no CUDA device: bench.py measures the CUDA path only (no CPU fallback)"}))
             return 1
-        res = run_b200(args)
+        if args.impl == "torch_gpu":
+            res = run_torch_gpu(args)
+        elif args.config == "c2":
+            res = run_c2(args)
+        else:
+            res = run_b200(args)
     if res is not None:
         print(json.dumps(res))
     return 0

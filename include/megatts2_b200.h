@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MTTS_ABI_VERSION 1
+#define MTTS_ABI_VERSION 2
 
 typedef enum {
   MTTS_OK = 0,
@@ -50,6 +50,16 @@ int mtts_profile_split(double* out6);
  * end synchronises and writes a text table "launcher launches total_ms share" into buf */
 int mtts_trace_begin(void* stream);
 int mtts_trace_end(char* buf, int32_t buf_len);
+
+/* Tensor-core operand formats.  Both give fp32-grade results (the tests hold them to the same bars):
+ *   BF16X3: x = x1 + x2 + x3 (bf16), products x1w1 + x1w2 + x2w1 + x2w2 + x1w3 + x3w1  -> 6 MMAs, fp32 range
+ *   F16X2 : x = x1 + x2' * 2^-11 (fp16, residual stored scaled so it stays in the normal range), products
+ *           x1w1 + (x1w2' + x2'w1) * 2^-11 -> 3 MMAs, 22 significant bits per operand; |x| must be <= 65504.
+ * An activation outside the fp16 range poisons its result (inf/NaN) and sets the int32 flag registered here for
+ * the current device (the caller owns the 4 bytes; NULL unbinds).  The Python layer checks it once per synthesis
+ * and reruns the batch on BF16X3. */
+enum { MTTS_TC_BF16X3 = 0, MTTS_TC_F16X2 = 1 };
+int mtts_tc_overflow_bind(int32_t* flag_dev);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };
@@ -99,19 +109,26 @@ typedef struct {
    * fill the GPU, K is split across CTAs into fp32 partials here and a second kernel reduces them in a fixed order and
    * applies the epilogue.  >= splits * B*Tout * Cout * 4 bytes; NULL -> never split. */
   void* tc_partial; int64_t tc_partial_bytes;
+  /* operand format of w_tc / the activation planes: MTTS_TC_BF16X3 (three bf16 planes, 6 MMAs per product) or
+   * MTTS_TC_F16X2 (two fp16 planes, residual scaled by 2^11, 3 MMAs per product; see mtts_tc_overflow_bind) */
+  int32_t tc_fmt;
+  /* leaky slope of post_act on the tensor-core engine is post_slope (as on the FFMA engine) */
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);
 
 /* Tensor-core linear layer (tcgen05, sm_100a): Y[M,N] = post(pre(X)[M,K] . W[N,K]^T + bias) (+ R) with
- * fp32-grade accuracy from a 3-way bf16 split of both operands and 6 MMAs (x1w1 + x1w2 + x2w1 + x2w2 +
- * x1w3 + x3w1, fp32 accumulation in TMEM).  w_planes: (3, N, K) bf16 row-major; scratch receives the
- * activation planes (mtts_linear_tc_scratch_bytes(rows_cap, K), rows_cap >= M).  K %% 8 == 0. */
+ * fp32-grade accuracy from split operands (fp32 accumulation in TMEM).  w_planes: (3, N, K) bf16 [BF16X3] or
+ * (2, N, K) fp16 [F16X2] row-major; scratch receives the activation planes
+ * (mtts_linear_tc_scratch_bytes(rows_cap, K), rows_cap >= M).  K %% 8 == 0. */
 int64_t mtts_linear_tc_scratch_bytes(int64_t rows_cap, int32_t K);
 int mtts_linear_tc_f32(const float* x, int32_t ldx, int64_t M, int32_t K, const void* w_planes, int32_t N,
                        const float* bias, const float* res, int32_t ldr, float* y, int32_t ldy,
                        int32_t pre_act, float pre_slope, int32_t post_act,
-                       void* scratch, int64_t scratch_bytes, int64_t rows_cap, void* stream);
+                       void* scratch, int64_t scratch_bytes, int64_t rows_cap, int32_t fmt, void* stream);
+/* fp32 (rows, C) with row stride ldx -> operand planes (3 | 2, rows, C) of `fmt` (the split the kernels apply to
+ * activations; the host side uses it to pack weights once).  C %% 4 == 0, x 16-byte aligned. */
+int mtts_split_planes_f32(const float* x, int32_t ldx, int64_t rows, int32_t C, void* planes, int32_t fmt, void* stream);
 
 /* LayerNorm over the last dim (nn.LayerNorm, eps 1e-5; modules/convnet.py:28-30,
  * modules/transformer.py:67-68, modules/mrte.py:136):
@@ -136,6 +153,7 @@ typedef struct {
   /* optional: write the output as three bf16 planes (row b*Tq + t, stride o_planes_ld) for a following
    * tensor-core GEMM; o may then be NULL */
   void* o_planes; int64_t o_plane_stride; int32_t o_planes_ld;
+  int32_t o_planes_fmt;                    /* MTTS_TC_BF16X3 | MTTS_TC_F16X2 */
 } mtts_attn_params;
 int mtts_attention_f32(const mtts_attn_params* p, void* stream);
 
@@ -195,6 +213,10 @@ int mtts_copy_strided_f32(const float* x, int64_t x_sb, int64_t x_st, int64_t x_
                           float* y, int64_t y_sb, int64_t y_st, int64_t y_sc,
                           int32_t B, int32_t T, int32_t C, int32_t pad_rep, void* stream);
 
+/* x (B, rows, L) contiguous: x[b, r, keep[b]:] = 0 in place - speechbrain HIFIGAN.mask_noise behind
+ * decode_batch(mel, mel_lens, hop_len) (reference call site models/megatts2.py:370). */
+int mtts_mask_tail_f32(float* x, int32_t B, int32_t rows, int32_t L, const int32_t* keep, void* stream);
+
 /* ------------------------------------------------------------------------------------------
  * Composite drivers: whole sub-networks enqueued by one call (C++ launch loop, no Python
  * per-kernel overhead).  Weight pointers refer to PRE-PACKED device buffers owned by the
@@ -213,7 +235,7 @@ typedef struct {
 
 typedef struct {
   int32_t n_layers, d_model, n_heads, ff_dim, conv_ff;
-  int32_t engine;                      /* 0: fp32 FFMA everywhere; 1: tcgen05 bf16x3 for GEMMs with M >= 128 */
+  int32_t engine;                      /* 0: fp32 FFMA everywhere; tcgen05 for GEMMs with M >= 128: 1 = BF16X3, 2 = F16X2 operands */
   const mtts_encoder_layer* layers;    /* HOST array of n_layers entries */
 } mtts_encoder;
 
@@ -275,7 +297,7 @@ typedef struct { const float *w, *b, *ln_g, *ln_b; const void* w_tc; } mtts_conv
 
 typedef struct {
   int32_t in_channels, out_channels, hidden, k, n_stacks, n_blocks;
-  int32_t engine;                      /* 0: fp32 FFMA; 1: tcgen05 bf16x3 for the eligible convs */
+  int32_t engine;                      /* 0: fp32 FFMA; tcgen05 for the eligible convs: 1 = BF16X3, 2 = F16X2 */
   const float *w_first, *b_first;      /* packed (k, Cin, hidden) */
   const float *w_last, *b_last;        /* packed (k, hidden, Cout) */
   const mtts_conv_block* blocks;       /* HOST array [n_stacks*n_blocks] */

@@ -9,7 +9,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libmegatts2_b200.so")
 
+ABI_VERSION = 2
 ACT_NONE, ACT_RELU, ACT_LEAKY, ACT_TANH = 0, 1, 2, 3
+TC_BF16X3, TC_F16X2 = 0, 1
 PAD_ZERO, PAD_REFLECT, PAD_REPLICATE = 0, 1, 2
 
 vp, i32, i64, f32 = C.c_void_p, C.c_int32, C.c_int64, C.c_float
@@ -33,6 +35,7 @@ class ConvParams(C.Structure):
         ("tc_presplit", i32), ("tc_out_planes", vp), ("tc_out_plane_stride", i64),
         ("tc_out_ld", i32), ("tc_out_tp", i32), ("tc_out_hl", i32), ("tc_out_act", i32), ("tc_out_slope", f32),
         ("tc_partial", vp), ("tc_partial_bytes", i64),
+        ("tc_fmt", i32),
     ]
 
 
@@ -45,7 +48,7 @@ class AttnParams(C.Structure):
         ("mask", vp), ("mask_sb", i64), ("mask_sh", i64), ("mask_sq", i64),
         ("B", i32), ("H", i32), ("Tq", i32), ("Tk", i32), ("dh", i32),
         ("scale", f32),
-        ("o_planes", vp), ("o_plane_stride", i64), ("o_planes_ld", i32),
+        ("o_planes", vp), ("o_plane_stride", i64), ("o_planes_ld", i32), ("o_planes_fmt", i32),
     ]
 
 
@@ -112,7 +115,10 @@ SIGNATURES = {
     "mtts_trace_end": (C.c_int, [C.c_char_p, i32]),
     "mtts_conv1d_f32": (C.c_int, [C.POINTER(ConvParams), vp]),
     "mtts_linear_tc_scratch_bytes": (i64, [i64, i32]),
-    "mtts_linear_tc_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, vp, i64, i64, vp]),
+    "mtts_linear_tc_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp, vp, i32, vp, i32, i32, f32, i32, vp, i64, i64, i32, vp]),
+    "mtts_split_planes_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp]),
+    "mtts_tc_overflow_bind": (C.c_int, [vp]),
+    "mtts_mask_tail_f32": (C.c_int, [vp, i32, i32, i32, vp, vp]),
     "mtts_layernorm_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, f32, i32, i32, vp]),
     "mtts_attention_f32": (C.c_int, [C.POINTER(AttnParams), vp]),
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),
@@ -159,7 +165,7 @@ def lib():
             fn = getattr(handle, name)     # AttributeError if the symbol is missing
             fn.restype = res
             fn.argtypes = args
-        if handle.mtts_abi_version() != 1:
+        if handle.mtts_abi_version() != ABI_VERSION:
             raise RuntimeError("libmegatts2_b200.so ABI version mismatch")
         _lib = handle
     return _lib

@@ -140,6 +140,10 @@ int mtts_length_regulate_f32(const float* x, int64_t x_sb, int32_t ldx, const in
   return length_regulate(x, x_sb, ldx, dur, dur_ld, B, Tp, D, L_out, y, y_sb, ldy, totals, (cudaStream_t)stream);
 }
 
+int mtts_mask_tail_f32(float* x, int32_t B, int32_t rows, int32_t L, const int32_t* keep, void* stream) {
+  return mask_tail(x, B, rows, L, keep, (cudaStream_t)stream);
+}
+
 int mtts_copy_strided_f32(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc, float* y, int64_t y_sb, int64_t y_st,
                           int64_t y_sc, int32_t B, int32_t T, int32_t C, int32_t pad_rep, void* stream) {
   return copy_strided(x, x_sb, x_st, x_sc, y, y_sb, y_st, y_sc, B, T, C, pad_rep, (cudaStream_t)stream);

@@ -1,6 +1,10 @@
 // Tensor-core tap-GEMM: every stride-1 Conv1d / ConvTranspose1d (2-tap form) / Linear (k = 1) on tcgen05 with fp32-grade
-// accuracy: both operands are split into three bf16 planes (x = x1 + x2 + x3 to 2^-24) and the six products whose
-// weight is >= 2^-16 are issued as bf16 MMAs into two TMEM accumulators (x1*w1 | the five corrections).
+// accuracy from split operands and two TMEM accumulators (leading product | corrections):
+//   NP = 3 (bf16x3): x = x1 + x2 + x3 in bf16 (to 2^-24); the six products whose weight is >= 2^-16 are issued.
+//   NP = 2 (f16x2):  x = x1 + x2' * 2^-11 in fp16 (the residual is stored scaled by 2^11, so it stays a normal fp16 number
+//                    whenever x is); three products x1*w1 | x1*w2' + x2'*w1, the correction accumulator is scaled by 2^-11
+//                    in the epilogue.  22 significant bits per operand: the dropped x2*w2 term is 2^-22 relative, below
+//                    the rounding noise of an fp32 dot product; half the MMAs and two thirds of the operand bytes.
 // Eligible wherever Cin % 8 == 0, Cin >= 32, Cout in {32, 64, >= 128 and % 32 == 0} and B*T >= 128; everything else
 // stays on the exact FFMA engine (tapconv.cu).  Reference layers: modules/convnet.py:13-18, modules/transformer.py:16-102,
 // the speechbrain HiFi-GAN generator (ResBlock1 convs, ConvTranspose1d upsamplers).
@@ -33,23 +37,24 @@ struct ConvTcArgs {
   const float* bias;
   const float* res; int64_t res_sb; int32_t ldr;
   float* y; int64_t y_sb; int32_t ldy;
-  int32_t post_act; float out_scale; int32_t accumulate;
+  int32_t post_act; float post_slope; float out_scale; int32_t accumulate;
   int64_t out_shift, ybe;      // transposed-conv form: element offset of the output and valid range per batch item
   // optional bf16x3 copy of the result for the next tensor-core layer
   __nv_bfloat16* op; int64_t op_stride; int32_t op_ld, op_tp, op_hl, op_act; float op_slope;
   // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
   int32_t splits; float* partial;
+  int32_t fmt; int32_t* ovf;   // operand format of the plane output (== the kernel's own NP) and the f16 range flag
 };
 
 // PAIR = 1: two CTAs of a cluster run one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of
 // the activations and HALF of the weight tile, so the L2 -> SM traffic per FLOP drops by a quarter
-template <int BN, int SWB, int PAIR = 0>
+template <int BN, int SWB, int PAIR = 0, int NP = 3>
 struct ConvTcCfg {
   static constexpr int BK = SWB / 2;                       // bf16 elements per swizzled row
   static constexpr int A_PLANE = 128 * SWB;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by one CTA
   static constexpr int B_PLANE = B_ROWS * SWB;
-  static constexpr int STAGE = 3 * (A_PLANE + B_PLANE);
+  static constexpr int STAGE = NP * (A_PLANE + B_PLANE);
   static constexpr int EPI_STAGE = 8 * 32 * 20 * 4;          // epilogue transpose buffers: 8 warps x [32 rows][20 floats]
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
@@ -58,10 +63,10 @@ struct ConvTcCfg {
   static constexpr int TMEM_COLS = NACC * 2 * BN < 32 ? 32 : NACC * 2 * BN;   // NACC x (main + correction) x BN
 };
 
-template <int BN, int SWB, int PAIR>
+template <int BN, int SWB, int PAIR, int NP>
 __global__ void __launch_bounds__(384, 1)
-conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
-  using Cfg = ConvTcCfg<BN, SWB, PAIR>;
+conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
+  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP>;
   constexpr int BM = PAIR ? 256 : 128;                     // rows of one (pair) tile
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a CTA or a CTA pair)
@@ -85,7 +90,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
 
   if (warp == 0 && lane == 0) {
 #pragma unroll
-    for (int i = 0; i < 3; ++i) {
+    for (int i = 0; i < NP; ++i) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.a[i]) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&maps.b[i]) : "memory");
     }
@@ -119,8 +124,8 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == 0) {
-    // ================= TMA producer: the whole warp walks the pipeline; lanes 0..5 each issue ONE of the six
-    // bulk copies of a K-slab (A p0..p2, B p0..p2) so the copies are issued concurrently - with one issuing
+    // ================= TMA producer: the whole warp walks the pipeline; lanes 0..2*NP-1 each issue ONE of the
+    // bulk copies of a K-slab (A planes, B planes) so the copies are issued concurrently - with one issuing
     // thread the ~6 x 100-150 cycles of issue latency per slab bound the small-channel convs
     int stage = 0, phase = 0;
     for (int item = worker; item < num_tiles; item += nworkers) {
@@ -133,29 +138,31 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
         const int j = kb / ncb, cb = kb - j * ncb;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
         const uint32_t sa = smem_base + stage * Cfg::STAGE;
-        const uint32_t sb = sa + 3 * Cfg::A_PLANE;
+        const uint32_t sb = sa + NP * Cfg::A_PLANE;
         if constexpr (PAIR) {
           // both CTAs' bytes are counted on the LEADER's barrier (the leader issues the MMAs for the pair)
           const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);
           if (lane == 0 && crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE);
           __syncwarp();
-          if (lane < 3) tma_load_3d_2sm(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
-          else if (lane < 6)
-            tma_load_2d_2sm(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK,
+          if (lane < NP) tma_load_3d_2sm(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
+          else if (lane < 2 * NP)
+            tma_load_2d_2sm(sb + (lane - NP) * Cfg::B_PLANE, &maps.b[lane - NP], fb, cb * Cfg::BK,
                             j * g.Cout + nb * BN + (int)crank * Cfg::B_ROWS);
         } else {
           const uint32_t fb = full_bar + 8 * stage;
           if (lane == 0) mbar_expect_tx(fb, Cfg::STAGE);
           __syncwarp();
-          if (lane < 3) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
-          else if (lane < 6) tma_load_2d(sb + (lane - 3) * Cfg::B_PLANE, &maps.b[lane - 3], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+          if (lane < NP) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
+          else if (lane < 2 * NP) tma_load_2d(sb + (lane - NP) * Cfg::B_PLANE, &maps.b[lane - NP], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
     if (lane == 0 && crank == 0) {   // ================= MMA issuer (the leader CTA issues for a pair) =================
-      const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      // instruction descriptor: D = f32, A / B = bf16 (1) or f16 (0), K-major, N >> 3, M >> 4
+      const uint32_t ab = NP == 3 ? ((1u << 7) | (1u << 10)) : 0u;
+      const uint32_t idesc = (1u << 4) | ab | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint64_t desc_base = umma_desc_kmajor<SWB>(0u);      // everything except the start address
       int stage = 0, phase = 0, it = 0;
       for (int item = worker; item < num_tiles; item += nworkers, ++it) {
@@ -171,14 +178,25 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
           tc_fence_after();
           // descriptors: constant high word, low word = (smem address >> 4); planes / k-steps are plain adds
           const uint64_t a0 = desc_base | (uint64_t)(((smem_base + stage * Cfg::STAGE) >> 4) & 0x3FFF);
-          const uint64_t b0 = a0 + (3 * Cfg::A_PLANE >> 4);
+          const uint64_t b0 = a0 + (NP * Cfg::A_PLANE >> 4);
           const uint32_t first = (kb == kb0) ? 0u : 1u;
 #pragma unroll
           for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
             const uint64_t a1 = a0 + 2 * ks, a2 = a1 + (Cfg::A_PLANE >> 4), a3 = a2 + (Cfg::A_PLANE >> 4);
             const uint64_t b1 = b0 + 2 * ks, b2 = b1 + (Cfg::B_PLANE >> 4), b3 = b2 + (Cfg::B_PLANE >> 4);
             const uint32_t f = (ks == 0) ? first : 1u;
-            if constexpr (PAIR) {
+            if constexpr (NP == 2) {
+              (void)a3; (void)b3;
+              if constexpr (PAIR) {
+                tc_mma_bf16_2sm(d_corr, a1, b2, idesc, f);    // x1 w2'
+                tc_mma_bf16_2sm(d_corr, a2, b1, idesc, 1u);   // x2' w1
+                tc_mma_bf16_2sm(d_main, a1, b1, idesc, f);    // x1 w1
+              } else {
+                tc_mma_bf16(d_corr, a1, b2, idesc, f);
+                tc_mma_bf16(d_corr, a2, b1, idesc, 1u);
+                tc_mma_bf16(d_main, a1, b1, idesc, f);
+              }
+            } else if constexpr (PAIR) {
               tc_mma_bf16_2sm(d_corr, a2, b2, idesc, f);
               tc_mma_bf16_2sm(d_corr, a1, b3, idesc, 1u);
               tc_mma_bf16_2sm(d_corr, a3, b1, idesc, 1u);
@@ -209,6 +227,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
     // ================= epilogue: 8 warps, two per TMEM lane quarter, 16-column units =================
     // (the small-channel convs are epilogue-bound: per output element there is more CUDA-core work than
     //  tensor-pipe work, so the epilogue gets as many warps as the register file allows)
+    constexpr float CS = NP == 2 ? F16X2_INV_SCALE : 1.0f;   // weight of the correction accumulator (exact: a power of two)
     const int ew = warp - 4;                      // 0..7
     const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
     const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
@@ -255,10 +274,10 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
 #pragma unroll
         for (int j = 0; j < 4; ++j)
           *reinterpret_cast<float4*>(stg + lane * 20 + 4 * j) =
-              make_float4(__uint_as_float(r[4 * j + 0]) + __uint_as_float(rc[4 * j + 0]),
-                          __uint_as_float(r[4 * j + 1]) + __uint_as_float(rc[4 * j + 1]),
-                          __uint_as_float(r[4 * j + 2]) + __uint_as_float(rc[4 * j + 2]),
-                          __uint_as_float(r[4 * j + 3]) + __uint_as_float(rc[4 * j + 3]));
+              make_float4(fmaf(__uint_as_float(rc[4 * j + 0]), CS, __uint_as_float(r[4 * j + 0])),
+                          fmaf(__uint_as_float(rc[4 * j + 1]), CS, __uint_as_float(r[4 * j + 1])),
+                          fmaf(__uint_as_float(rc[4 * j + 2]), CS, __uint_as_float(r[4 * j + 2])),
+                          fmaf(__uint_as_float(rc[4 * j + 3]), CS, __uint_as_float(r[4 * j + 3])));
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
@@ -272,7 +291,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
           float v[4] = {a4.x + bvec.x, a4.y + bvec.y, a4.z + bvec.z, a4.w + bvec.w};
           if (g.post_act != MTTS_ACT_NONE) {
 #pragma unroll
-            for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, 0.f);
+            for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, g.post_slope);
           }
           v[0] = (v[0] + rv[i].x) * g.out_scale + ov[i].x;
           v[1] = (v[1] + rv[i].y) * g.out_scale + ov[i].y;
@@ -288,7 +307,7 @@ conv_bf16x3_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) 
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.op_act, g.op_slope);
             }
-            store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v);
+            store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v, NP == 2 ? MTTS_TC_F16X2 : MTTS_TC_BF16X3, g.ovf);
           }
         }
         __syncwarp();   // the staging buffer is reused by the next unit
@@ -340,7 +359,7 @@ tc_splitk_reduce_kernel(const ConvTcArgs g, int64_t total4) {
   }
   if (g.post_act != MTTS_ACT_NONE) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, 0.f);
+    for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.post_act, g.post_slope);
   }
   float4 rv = make_float4(0.f, 0.f, 0.f, 0.f), ov = rv;
   if (g.res) rv = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
@@ -355,15 +374,15 @@ tc_splitk_reduce_kernel(const ConvTcArgs g, int64_t total4) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.op_act, g.op_slope);
     }
-    store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v);
+    store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v, g.fmt, g.ovf);
   }
 }
 
-// fp32 (B,T,C) -> three bf16 planes (B, Tp = T + hl + hr, C): padding materialised, pre-activation applied
+// fp32 (B,T,C) -> operand planes (B, Tp = T + hl + hr, C): padding materialised, pre-activation applied
 __global__ void __launch_bounds__(256)
-split_pad_bf16x3_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int C, int hl, int Tp, int pad_mode,
-                        int pre_act, float slope, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
-                        int64_t total4) {
+split_pad_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int C, int hl, int Tp, int pad_mode,
+                 int pre_act, float slope, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
+                 int64_t total4, int fmt, int32_t* ovf) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int cq = C >> 2;
@@ -386,24 +405,9 @@ split_pad_bf16x3_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int 
     const float4 v = *reinterpret_cast<const float4*>(x + (int64_t)b * x_sb + (int64_t)ti * ldx + c);
     f[0] = v.x; f[1] = v.y; f[2] = v.z; f[3] = v.w;
   }
-  __nv_bfloat16 p[3][4];
 #pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float a = act_apply(f[e], pre_act, slope);
-    p[0][e] = __float2bfloat16_rn(a);
-    a -= __bfloat162float(p[0][e]);
-    p[1][e] = __float2bfloat16_rn(a);
-    a -= __bfloat162float(p[1][e]);
-    p[2][e] = __float2bfloat16_rn(a);
-  }
-  const int64_t off = ((int64_t)b * Tp + u) * C + c;
-#pragma unroll
-  for (int qn = 0; qn < 3; ++qn) {
-    uint2 o;
-    o.x = (uint32_t)__bfloat16_as_ushort(p[qn][0]) | ((uint32_t)__bfloat16_as_ushort(p[qn][1]) << 16);
-    o.y = (uint32_t)__bfloat16_as_ushort(p[qn][2]) | ((uint32_t)__bfloat16_as_ushort(p[qn][3]) << 16);
-    *reinterpret_cast<uint2*>(planes + qn * plane_stride + off) = o;
-  }
+  for (int e = 0; e < 4; ++e) f[e] = act_apply(f[e], pre_act, slope);
+  store_planes4(planes, plane_stride, ((int64_t)b * Tp + u) * C + c, f, fmt, ovf);
 }
 
 // Materialise the padding rows of plane buffers whose interior rows were written by a producer epilogue:
@@ -448,73 +452,132 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 static EncodeTiledFn g_enc = nullptr;
-static std::mutex g_ctc_mu;
-static int g_ctc_sms = 0;
+static std::mutex g_ctc_mu;          // guards g_enc, the descriptor cache and the per-device table (not the launches)
+
+// per-device state: SM count, which kernel instantiations have had their shared-memory attribute raised (the attribute
+// is per device), and the caller-registered f16 range flag
+constexpr int MAX_DEV = 64;
+struct DevState { int sms = 0; uint32_t attr_done = 0; int32_t* ovf = nullptr; };
+static DevState g_dev[MAX_DEV];
+
+int cur_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev < 0 || dev >= MAX_DEV ? 0 : dev;
+}
+int cur_device_sms() {
+  const int dev = cur_device();
+  if (!g_dev[dev].sms) {
+    int n = 0;
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    g_dev[dev].sms = n > 0 ? n : 1;
+  }
+  return g_dev[dev].sms;
+}
+int32_t* tc_ovf_ptr() { return g_dev[cur_device()].ovf; }
+int tc_overflow_bind(int32_t* flag) {
+  g_dev[cur_device()].ovf = flag;
+  return 0;
+}
+
+// tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
+// tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
+// too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; };
+static const CtcEnv& ctc_env() {
+  static const CtcEnv env = [] {
+    CtcEnv e;
+    const char* ke = getenv("MEGATTS2_TC_SPLITK");
+    const char* me = getenv("MEGATTS2_TC_SPLITK_MAX");
+    const char* ge = getenv("MEGATTS2_TC_SPLITK_MARGIN");
+    const char* pe = getenv("MEGATTS2_TC_PAIR");
+    const char* se = getenv("MEGATTS2_TC_SWB64");
+    e.splitk = !(ke && ke[0] == '0');
+    e.sk_max = me ? atoi(me) : 8;
+    e.margin = ge ? atof(ge) : 0.85;
+    e.pair_mode = pe ? atoi(pe) : 1;
+    e.swb64 = se && se[0] == '1';
+    return e;
+  }();
+  return env;
+}
 
 struct CMapKey {
-  const void* p; uint64_t d0, d1, d2, b0, b1; int swb;
+  const void* p; uint64_t d0, d1, d2, b0, b1; int swb, dt;
   bool operator==(const CMapKey& o) const {
-    return p == o.p && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && swb == o.swb;
+    return p == o.p && d0 == o.d0 && d1 == o.d1 && d2 == o.d2 && b0 == o.b0 && b1 == o.b1 && swb == o.swb && dt == o.dt;
   }
 };
 struct CMapKeyHash {
   size_t operator()(const CMapKey& k) const {
     uint64_t h = (uint64_t)k.p;
     h = h * 0x9E3779B97F4A7C15ull + k.d0; h = h * 0x9E3779B97F4A7C15ull + k.d1; h = h * 0x9E3779B97F4A7C15ull + k.d2;
-    h = h * 0x9E3779B97F4A7C15ull + k.b0 * 131 + k.b1 * 7 + k.swb;
+    h = h * 0x9E3779B97F4A7C15ull + k.b0 * 131 + k.b1 * 7 + k.swb + 1000 * k.dt;
     return (size_t)h;
   }
 };
-static std::unordered_map<CMapKey, CUtensorMap, CMapKeyHash> g_cmaps;
+// Descriptor cache: keyed by (pointer, dims, box, swizzle, dtype); a descriptor holds nothing but those, so a stale entry
+// for a freed-and-reused address is still correct.  Bounded: when full, the older half (by insertion order) is dropped.
+static std::unordered_map<CMapKey, std::pair<CUtensorMap, uint64_t>, CMapKeyHash> g_cmaps;
+static uint64_t g_cmap_tick = 0;
+constexpr size_t CMAP_CAP = 16384;
 
-static int ctc_init() {
+static int ctc_init_locked() {
   if (g_enc) return 0;
   void* fn = nullptr;
   cudaDriverEntryPointQueryResult qres;
   if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn)
     return fail(MTTS_ERR_CUDA, "%s: cuTensorMapEncodeTiled not available", "conv_tc");
   g_enc = (EncodeTiledFn)fn;
-  int dev = 0;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&g_ctc_sms, cudaDevAttrMultiProcessorCount, dev);
   return 0;
 }
 
-// bf16 tensor (d2, d1, d0) row-major, box (1, b1, b0), SWB-byte swizzle; rank 2 when d2 == 0
-static int cmap_get(const void* p, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, int swb,
+// 2-byte-element tensor (d2, d1, d0) row-major, box (1, b1, b0), SWB-byte swizzle; rank 2 when d2 == 0
+static int cmap_get(const void* p, uint64_t d0, uint64_t d1, uint64_t d2, uint32_t b0, uint32_t b1, int swb, int fmt,
                     CUtensorMap* out) {
-  CMapKey key{p, d0, d1, d2, b0, b1, swb};
+  std::lock_guard<std::mutex> lk(g_ctc_mu);
+  MTTS_TRY(ctc_init_locked());
+  CMapKey key{p, d0, d1, d2, b0, b1, swb, fmt};
   auto itf = g_cmaps.find(key);
-  if (itf != g_cmaps.end()) { *out = itf->second; return 0; }
+  if (itf != g_cmaps.end()) { *out = itf->second.first; return 0; }
   const int rank = d2 ? 3 : 2;
   cuuint64_t dims[3] = {d0, d1, d2 ? d2 : 1};
   cuuint64_t strides[2] = {d0 * 2, d0 * d1 * 2};
   cuuint32_t box[3] = {b0, b1, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   CUtensorMap m;
-  CUresult r = g_enc(&m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, const_cast<void*>(p), dims, strides, box, estr,
-                     CU_TENSOR_MAP_INTERLEAVE_NONE, swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
-                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  CUresult r = g_enc(&m, fmt == MTTS_TC_F16X2 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank,
+                     const_cast<void*>(p), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                     swb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(MTTS_ERR_CUDA, "%s: cuTensorMapEncodeTiled failed: %lld", "conv_tc", (long long)r);
-  if (g_cmaps.size() > 8192) g_cmaps.clear();
-  g_cmaps[key] = m;
+  if (g_cmaps.size() >= CMAP_CAP) {
+    const uint64_t cut = g_cmap_tick - CMAP_CAP / 2;
+    for (auto it = g_cmaps.begin(); it != g_cmaps.end();) it = it->second.second < cut ? g_cmaps.erase(it) : ++it;
+  }
+  g_cmaps[key] = {m, g_cmap_tick++};
   *out = m;
   return 0;
 }
 
-template <int BN, int SWB, int PAIR = 0>
+template <int BN, int SWB, int PAIR, int NP>
 static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStream_t st) {
-  using Cfg = ConvTcCfg<BN, SWB, PAIR>;
-  static bool attr = false;
-  if (!attr) {
+  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP>;
+  // one bit per instantiation in the per-device table (the max-dynamic-shared-memory attribute is per device)
+  constexpr int slot = (BN == 128 ? 0 : BN == 64 ? 1 : 2) + 3 * (SWB == 128 ? 0 : 1) + 6 * PAIR + 12 * (NP == 3 ? 0 : 1);
+  static_assert(slot < 32, "attribute slots");
+  const int dev = cur_device();
+  const int sms = cur_device_sms();
+  if (!(g_dev[dev].attr_done & (1u << slot))) {
+    std::lock_guard<std::mutex> lk(g_ctc_mu);
     cudaError_t e =
-        cudaFuncSetAttribute(conv_bf16x3_kernel<BN, SWB, PAIR>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, SWB, PAIR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "conv_tc", (long long)e);
-    attr = true;
+    g_dev[dev].attr_done |= (1u << slot);
   }
   const int64_t tiles = (int64_t)a.B * cdiv64(a.T, PAIR ? 256 : 128) * cdiv64(a.Cout, BN) * a.splits;
   if (PAIR) {
-    const int64_t pairs = tiles < g_ctc_sms / 2 ? tiles : g_ctc_sms / 2;
+    const int64_t pairs = tiles < sms / 2 ? tiles : sms / 2;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(2 * pairs));
     cfg.blockDim = dim3(384);
@@ -524,18 +587,30 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_bf16x3_kernel<BN, SWB, PAIR>, maps, a);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SWB, PAIR, NP>, maps, a);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cluster launch failed: %lld", "conv_tc", (long long)e);
   } else {
-    const int grid = (int)(tiles < g_ctc_sms ? tiles : g_ctc_sms);
-    conv_bf16x3_kernel<BN, SWB, PAIR><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    conv_tc_kernel<BN, SWB, PAIR, NP><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
   }
   MTTS_CHECK_LAUNCH();
   return 0;
 }
 
+template <int NP>
+static int conv_tc_dispatch(const ConvTcMaps& maps, const ConvTcArgs& a, int BN, int SWB, bool pair, cudaStream_t st) {
+  if (pair) return SWB == 128 ? conv_tc_launch<128, 128, 1, NP>(maps, a, st) : conv_tc_launch<128, 64, 1, NP>(maps, a, st);
+  if (SWB == 64 && BN == 128) return conv_tc_launch<128, 64, 0, NP>(maps, a, st);
+  if (SWB == 64 && BN == 64) return conv_tc_launch<64, 64, 0, NP>(maps, a, st);
+  if (SWB == 64) return conv_tc_launch<32, 64, 0, NP>(maps, a, st);
+  if (BN == 128) return conv_tc_launch<128, 128, 0, NP>(maps, a, st);
+  if (BN == 64) return conv_tc_launch<64, 128, 0, NP>(maps, a, st);
+  return conv_tc_launch<32, 128, 0, NP>(maps, a, st);
+}
+
 bool conv_tc_eligible(const mtts_conv_params& p) {
   if (!p.w_tc || !p.tc_scratch) return false;
+  if (p.tc_fmt != MTTS_TC_BF16X3 && p.tc_fmt != MTTS_TC_F16X2) return false;
   if (p.stride != 1 || p.in_lens) return false;
   if (p.out_shift != 0 && (p.out_shift % 4 != 0 || p.y_batch_elems % 4 != 0 || p.res || p.accumulate || p.tc_out_planes || !p.y))
     return false;
@@ -559,8 +634,11 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
 }
 
 int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
-  std::lock_guard<std::mutex> lk(g_ctc_mu);
-  MTTS_TRY(ctc_init());
+  const CtcEnv& env = ctc_env();
+  const int sms = cur_device_sms();
+  const int fmt = p.tc_fmt;
+  const int np = fmt == MTTS_TC_F16X2 ? 2 : 3;
+  int32_t* ovf = tc_ovf_ptr();
   const int halo = p.dil * (p.k - 1);
   const int hl = p.pad, Tp = p.Tout + halo;
   const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : Tp;     // descriptor rows (>= Tp)
@@ -568,9 +646,9 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
   if (!p.tc_presplit) {
     const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
-    split_pad_bf16x3_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
-                                                                          p.pad_mode, p.pre_act, p.pre_slope, planes,
-                                                                          plane_stride, total4);
+    split_pad_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
+                                                                   p.pad_mode, p.pre_act, p.pre_slope, planes, plane_stride,
+                                                                   total4, fmt, ovf);
     MTTS_CHECK_LAUNCH();
   }
   int SWB = p.Cin >= 64 ? 128 : 64;
@@ -583,7 +661,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
     for (int i = 0; i < 3; ++i) {
       if (cands[i] > p.Cout) continue;
       BN = cands[i];
-      if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(g_ctc_sms * 4) / 5) break;
+      if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(sms * 4) / 5) break;
     }
   }
   // split-K for dense layers with too few output tiles to fill the GPU (the early steps of the AR loops, the N = 1024
@@ -591,25 +669,21 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   // every k-step, so K is split across CTAs at full tile width instead and a second kernel reduces the partials
   int splits = 1;
   {
-    const char* ke = getenv("MEGATTS2_TC_SPLITK");
     const int64_t rows = (int64_t)p.B * p.Tout;
     const int64_t t128 = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, 128);
     const int nk = (p.Cin + 63) / 64;
-    if (!(ke && ke[0] == '0') && SWB == 128 && p.k == 1 && p.out_shift == 0 && p.tc_partial && p.Cout >= 128 &&
-        t128 < (int64_t)(g_ctc_sms * 4) / 5) {
-      int sk = (int)(g_ctc_sms / t128);
-      const char* me = getenv("MEGATTS2_TC_SPLITK_MAX");
-      const char* ge = getenv("MEGATTS2_TC_SPLITK_MARGIN");
-      const int sk_max = me ? atoi(me) : 8;
-      const double margin = ge ? atof(ge) : 0.85;
-      if (sk > sk_max) sk = sk_max;
+    if (env.splitk && SWB == 128 && p.k == 1 && p.out_shift == 0 && p.tc_partial && p.Cout >= 128 &&
+        t128 < (int64_t)(sms * 4) / 5) {
+      int sk = (int)(sms / t128);
+      if (sk > env.sk_max) sk = env.sk_max;
       if (sk > nk / 2) sk = nk / 2;
       if (sk >= 2 && (int64_t)sk * rows * p.Cout * 4 <= p.tc_partial_bytes) {
         const int64_t tiles_bn = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, BN);
-        const double waves = (double)cdiv64(tiles_bn, g_ctc_sms);
-        const double cost_now = waves * nk * 24.0 * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
-        const double cost_split = (double)cdiv64(nk, sk) * 24.0 * 65.0 + 9000.0;             // + reduction kernel
-        if (cost_split < margin * cost_now) { splits = sk; BN = 128; }
+        const double waves = (double)cdiv64(tiles_bn, sms);
+        const double mmas = 4.0 * (2 * np);                                                 // MMAs per 64-wide K-slab
+        const double cost_now = waves * nk * mmas * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
+        const double cost_split = (double)cdiv64(nk, sk) * mmas * 65.0 + 9000.0;             // + reduction kernel
+        if (cost_split < env.margin * cost_now) { splits = sk; BN = 128; }
       }
     }
   }
@@ -617,48 +691,54 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   // weight tile, so a quarter fewer bytes cross L2 -> SM and a quarter fewer operand bytes are read from shared memory
   // per FLOP.  Measured (tools/bench_tc_shapes.py): +1..3 % on the dense layers, -5 % on the ragged-T convolutions
   // (256-row tiles waste more of the last tile), so pairs are used for k = 1 only.
-  // Tuning switches (diagnostics): MEGATTS2_TC_PAIR = 0 | 1 | 2 (2: 32-wide K-slabs), MEGATTS2_TC_SWB64 = 1.
-  const char* pe = getenv("MEGATTS2_TC_PAIR");
-  const int pair_mode = pe ? atoi(pe) : 1;
-  const char* se = getenv("MEGATTS2_TC_SWB64");
-  if (se && se[0] == '1') SWB = 64;
+  if (env.swb64) SWB = 64;
   bool pair = false;
-  if (pair_mode && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || pair_mode >= 3)) {
+  if (env.pair_mode && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || env.pair_mode >= 3)) {
     const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
-    pair = t256 >= (int64_t)(g_ctc_sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
-    if (pair && (pair_mode == 2 || pair_mode == 4)) SWB = 64;      // 32-wide K-slabs: 5 stages of 36 KB instead of 2 of 72 KB
+    pair = t256 >= (int64_t)(sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
+    if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs
   }
   const int b_rows = pair ? BN / 2 : BN;
   ConvTcMaps maps;
-  for (int q = 0; q < 3; ++q) {
-    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2, 128, SWB, &maps.a[q]));
+  for (int q = 0; q < np; ++q) {
+    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2, 128, SWB, fmt, &maps.a[q]));
     MTTS_TRY(cmap_get((const __nv_bfloat16*)p.w_tc + (int64_t)q * p.k * p.Cout * p.Cin, (uint64_t)p.Cin,
-                      (uint64_t)p.k * p.Cout, 0, SWB / 2, b_rows, SWB, &maps.b[q]));
+                      (uint64_t)p.k * p.Cout, 0, SWB / 2, b_rows, SWB, fmt, &maps.b[q]));
   }
+  if (np == 2) { maps.a[2] = maps.a[1]; maps.b[2] = maps.b[1]; }
   ConvTcArgs a;
   a.B = p.B; a.T = p.Tout; a.Cin = p.Cin; a.Cout = p.Cout; a.k = p.k; a.dil = p.dil;
   a.bias = p.bias; a.res = p.res; a.res_sb = p.res_batch_stride; a.ldr = p.ldr;
   a.y = p.y; a.y_sb = p.y_batch_stride; a.ldy = p.ldy;
-  a.post_act = p.post_act; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
+  a.post_act = p.post_act; a.post_slope = p.post_slope; a.out_scale = p.out_scale; a.accumulate = p.accumulate;
   a.out_shift = p.out_shift; a.ybe = p.y_batch_elems ? p.y_batch_elems : (int64_t)p.Tout * p.ldy;
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
+  a.fmt = fmt; a.ovf = ovf;
   if (splits > 1) {
-    MTTS_TRY((conv_tc_launch<128, 128>(maps, a, st)));
+    MTTS_TRY(np == 2 ? (conv_tc_launch<128, 128, 0, 2>(maps, a, st)) : (conv_tc_launch<128, 128, 0, 3>(maps, a, st)));
     const int64_t total4 = (int64_t)p.B * p.Tout * p.Cout / 4;
     tc_splitk_reduce_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(a, total4);
     MTTS_CHECK_LAUNCH();
     return 0;
   }
-  if (pair) return SWB == 128 ? conv_tc_launch<128, 128, 1>(maps, a, st) : conv_tc_launch<128, 64, 1>(maps, a, st);
-  if (SWB == 64 && BN == 128) return conv_tc_launch<128, 64>(maps, a, st);
-  if (SWB == 64 && BN == 64) return conv_tc_launch<64, 64>(maps, a, st);
-  if (SWB == 64) return conv_tc_launch<32, 64>(maps, a, st);
-  if (BN == 128) return conv_tc_launch<128, 128>(maps, a, st);
-  if (BN == 64) return conv_tc_launch<64, 128>(maps, a, st);
-  return conv_tc_launch<32, 128>(maps, a, st);
+  return np == 2 ? conv_tc_dispatch<2>(maps, a, BN, SWB, pair, st) : conv_tc_dispatch<3>(maps, a, BN, SWB, pair, st);
+}
+
+// fp32 (rows, C) -> operand planes (3 | 2, rows, C): the activation split, exposed for packing weights on the device
+int split_planes(const float* x, int ldx, int64_t rows, int C, void* planes, int fmt, cudaStream_t st) {
+  MTTS_REQUIRE(x && planes && C > 0 && C % 4 == 0 && ldx % 4 == 0 && ((((uintptr_t)x) | ((uintptr_t)planes)) & 15) == 0, "bad arguments");
+  MTTS_REQUIRE(fmt == MTTS_TC_BF16X3 || fmt == MTTS_TC_F16X2, "unknown operand format");
+  if (rows <= 0) return 0;
+  MTTS_REQUIRE(rows < (int64_t)1 << 31, "too many rows");
+  const int64_t total4 = rows * C / 4;
+  split_pad_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(x, 0, ldx, (int)rows, C, 0, (int)rows, MTTS_PAD_ZERO, MTTS_ACT_NONE, 0.f,
+                                                                 reinterpret_cast<__nv_bfloat16*>(planes), rows * (int64_t)C, total4,
+                                                                 fmt, tc_ovf_ptr());
+  MTTS_CHECK_LAUNCH();
+  return 0;
 }
 
 // nn.Linear on the tensor-core engine = the k = 1 case of the tap-GEMM
@@ -666,12 +746,12 @@ int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K) { return 3 * rows_cap *
 
 int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,
               const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,
-              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, cudaStream_t st) {
+              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, int fmt, cudaStream_t st) {
   MTTS_REQUIRE(x && w_planes && y && scratch, "null pointer");
   mtts_conv_params p = linear_params(x, ldx, nullptr, bias, y, ldy, M, K, N);
   p.w = reinterpret_cast<const float*>(w_planes);     // unused on this path (non-null for validation only)
   p.res = res; p.ldr = ldr; p.pre_act = pre_act; p.pre_slope = pre_slope; p.post_act = post_act; p.out_scale = out_scale;
-  p.w_tc = w_planes; p.tc_scratch = scratch; p.tc_scratch_bytes = scratch_bytes; p.tc_rows_cap = rows_cap;
+  p.w_tc = w_planes; p.tc_scratch = scratch; p.tc_scratch_bytes = scratch_bytes; p.tc_rows_cap = rows_cap; p.tc_fmt = fmt;
   if (!conv_tc_eligible(p))
     return fail(MTTS_ERR_UNSUPPORTED, "%s: shape not eligible for the tensor-core engine (M=%lld N=%lld)", "linear_tc", M, N);
   return conv_tc(p, st);

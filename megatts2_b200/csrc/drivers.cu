@@ -33,22 +33,22 @@ int conv1d(const mtts_conv_params& p, cudaStream_t st) {
 // tensor-core context of a composite driver call: engine switch + scratch for activation planes
 struct ConvTc { int engine; void* scratch; int64_t bytes; };
 static inline void attach_tc(mtts_conv_params& p, const void* w_tc, const ConvTc* tc) {
-  if (tc && tc->engine == 1 && w_tc && tc->scratch) {
-    p.w_tc = w_tc; p.tc_scratch = tc->scratch; p.tc_scratch_bytes = tc->bytes;
+  if (tc && tc->engine >= 1 && w_tc && tc->scratch) {
+    p.w_tc = w_tc; p.tc_scratch = tc->scratch; p.tc_scratch_bytes = tc->bytes; p.tc_fmt = tc_fmt_of_engine(tc->engine);
   }
 }
 static inline int64_t conv_tc_scratch_need(int64_t B, int64_t Tp, int64_t C) { return 6 * B * Tp * C + 4096; }
 
 // scratch for the tensor-core engine's activation planes, carved once per driver call so that the
 // (cached) TMA descriptors keep hitting across the steps of an autoregressive loop
-struct TcScratch { void* p; int64_t bytes; int64_t rows_cap; };
+struct TcScratch { void* p; int64_t bytes; int64_t rows_cap; int fmt; };
 
 constexpr int64_t TC_PARTIAL_BYTES = 64ll << 20;
 static inline int64_t tc_planes_bytes(const mtts_encoder* e, int64_t rows_cap) {
   return align_up(6 * rows_cap * ((int64_t)e->d_model + e->ff_dim) + 8192, 1024);
 }
 static int64_t tc_scratch_bytes(const mtts_encoder* e, int64_t rows_cap) {
-  if (e->engine != 1) return 0;
+  if (e->engine < 1) return 0;
   const int kmax = e->ff_dim > e->d_model ? e->ff_dim : e->d_model;
   // conv-FF (k = 5): padded planes need 4 halo rows per sequence; rows_cap + 4*rows_cap covers any batch split
   if (e->conv_ff) return linear_tc_scratch_bytes(5 * rows_cap + 64, kmax) + 4096;
@@ -72,7 +72,7 @@ static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int
   p.res = res; p.ldr = ldr; p.post_act = post_act;
   p.tc_partial = partial; p.tc_partial_bytes = partial_bytes;
   p.w_tc = wtc; p.tc_scratch = planes; p.tc_scratch_bytes = 6 * tc->rows_cap * (int64_t)K + 4096; p.tc_rows_cap = tc->rows_cap;
-  p.tc_presplit = 1;
+  p.tc_presplit = 1; p.tc_fmt = tc->fmt;
   if (out_planes) {
     p.tc_out_planes = out_planes; p.tc_out_plane_stride = tc->rows_cap * (int64_t)out_ld; p.tc_out_ld = out_ld;
     p.tc_out_tp = (int32_t)tc->rows_cap; p.tc_out_hl = 0; p.tc_out_act = MTTS_ACT_NONE;
@@ -102,8 +102,8 @@ static int lin(const mtts_encoder* e, const TcScratch* tc, const float* x, int l
                int post_act, cudaStream_t st) {
   mtts_conv_params p = linear_params(x, ldx, w32, bias, y, ldy, M, K, N);
   p.res = res; p.ldr = ldr; p.post_act = post_act;
-  if (e->engine == 1 && tc && tc->p && wtc) {
-    p.w_tc = wtc; p.tc_scratch = tc->p; p.tc_scratch_bytes = tc->bytes; p.tc_rows_cap = tc->rows_cap;
+  if (e->engine >= 1 && tc && tc->p && wtc) {
+    p.w_tc = wtc; p.tc_scratch = tc->p; p.tc_scratch_bytes = tc->bytes; p.tc_rows_cap = tc->rows_cap; p.tc_fmt = tc->fmt;
   }
   return conv1d(p, st);
 }
@@ -135,7 +135,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
   const float* xin = x;
   // Fused plane flow (tensor-core engine, linear FF, M >= 128): LayerNorm / attention / the FF1 epilogue write
   // their result directly as bf16x3 planes, so no split pass and no fp32 round trip feeds the GEMMs.
-  bool fused = e->engine == 1 && !e->conv_ff && tc && tc->p && M >= 128 && D % 32 == 0 && F % 32 == 0 &&
+  bool fused = e->engine >= 1 && !e->conv_ff && tc && tc->p && M >= 128 && D % 32 == 0 && F % 32 == 0 &&
                tc->bytes >= tc_planes_bytes(e, tc->rows_cap) && tc->rows_cap >= M;
   for (int l = 0; fused && l < e->n_layers; ++l)
     fused = e->layers[l].w_qkv_tc && e->layers[l].w_o_tc && e->layers[l].w_ff1_tc && e->layers[l].w_ff2_tc;
@@ -145,7 +145,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
     Pa = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)tc->p) + 1023) & ~(uintptr_t)1023);
     Pb = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)(Pa + 3 * tc->rows_cap * (int64_t)D)) + 1023) & ~(uintptr_t)1023);
   }
-  const PlanesOut pa_out{Pa, tc ? tc->rows_cap * (int64_t)D : 0, D, MTTS_ACT_NONE, 0.f};
+  const PlanesOut pa_out{Pa, tc ? tc->rows_cap * (int64_t)D : 0, D, MTTS_ACT_NONE, 0.f, tc ? tc->fmt : 0, tc_ovf_ptr()};
   void* part = nullptr;
   int64_t part_bytes = 0;
   if (fused) tc_partial_area(e, tc, &part, &part_bytes);
@@ -169,7 +169,7 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
     if (!last) {
       ap.q = qkv; ap.q_sb = (int64_t)T * 3 * D; ap.q_st = 3 * D; ap.Tq = T;
       if (fused) {
-        ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D;
+        ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D; ap.o_planes_fmt = tc->fmt;
         MTTS_TRY(attention(ap, st));
         MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st, part, part_bytes));
         MTTS_TRY(layernorm_ex(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
@@ -255,7 +255,7 @@ static int plm_infer(const mtts_plm* m, const float* tc, int64_t tc_sb, int tc_l
   float* xl = top.take<float>((int64_t)B * D);
   float* logits = top.take<float>((int64_t)B * V);
   int64_t* codes = top.take<int64_t>((int64_t)B * (T + 1));
-  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T};
+  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T, tc_fmt_of_engine(m->enc.engine)};
   if (tcs.bytes) tcs.p = top.take<char>(tcs.bytes);
   const int64_t enc_off = align_up(top.off, 256);
   if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
@@ -302,7 +302,7 @@ static int adm_infer(const mtts_adm* m, const float* tc, int64_t tc_sb, int tc_l
   float* xl = top.take<float>((int64_t)B * D);
   float* tc_emb = top.take<float>((int64_t)B * T * m->tc_emb_dim);
   float* praw = top.take<float>((int64_t)B * (T + 1));
-  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T};
+  TcScratch tcs{nullptr, tc_scratch_bytes(&m->enc, (int64_t)B * T), (int64_t)B * T, tc_fmt_of_engine(m->enc.engine)};
   if (tcs.bytes) tcs.p = top.take<char>(tcs.bytes);
   const int64_t enc_off = align_up(top.off, 256);
   if (enc_off + encoder_ws_floats(&m->enc, B, T) * 4 > ws_bytes)
@@ -509,7 +509,7 @@ static int residual_stack(const mtts_conv_block* blocks, int n_stacks, int n_blo
 }
 
 static int64_t convnet_ws_floats(const mtts_convnet* n, int B, int T) {
-  return 3 * ((int64_t)B * T * n->hidden + 64) + (n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
+  return 3 * ((int64_t)B * T * n->hidden + 64) + (n->engine >= 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
 }
 
 static int convnet_forward(const mtts_convnet* n, const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb,
@@ -522,7 +522,7 @@ static int convnet_forward(const mtts_convnet* n, const float* x, int64_t x_sb, 
   StackBufs sb;
   sb.tmp = ar.take<float>(M * n->hidden);
   sb.h1 = ar.take<float>(M * n->hidden);
-  ConvTc tc{n->engine, nullptr, n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) : 0};
+  ConvTc tc{n->engine, nullptr, n->engine >= 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) : 0};
   if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet", ar.off);
   mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, xc, B, T, n->in_channels, n->hidden, n->k, 1, MTTS_PAD_ZERO);
@@ -543,7 +543,7 @@ static int cnd_mid_len(const mtts_convnet_double* n, int T) {
 static int64_t convnet_double_ws_floats(const mtts_convnet_double* n, int B, int T) {
   const int Tm = cnd_mid_len(n, T);
   return 4 * ((int64_t)B * T * n->hidden + 64) + 2 * ((int64_t)B * Tm * n->hidden + 64) +
-         (n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
+         (n->engine >= 1 ? conv_tc_scratch_need(B, T + n->k, n->hidden) / 4 + 64 : 0);
 }
 
 static int convnet_double_forward(const mtts_convnet_double* n, const float* x, int64_t x_sb, int ldx, float* y,
@@ -561,7 +561,7 @@ static int convnet_double_forward(const mtts_convnet_double* n, const float* x, 
   sb.h1 = ar.take<float>(M * H);
   float* xm = ar.take<float>(Mm * H);
   float* acc = ar.take<float>(Mm * H);
-  ConvTc tc{n->engine, nullptr, n->engine == 1 ? conv_tc_scratch_need(B, T + n->k, H) : 0};
+  ConvTc tc{n->engine, nullptr, n->engine >= 1 ? conv_tc_scratch_need(B, T + n->k, H) : 0};
   if (tc.bytes) tc.scratch = ar.take<char>(tc.bytes);
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "convnet_double", ar.off);
   mtts_conv_params p = conv_same_params(x, n->w_first, n->b_first, h0, B, T, n->in_channels, H, n->k, 1, MTTS_PAD_ZERO);
@@ -603,7 +603,7 @@ static int64_t hifigan_ws_floats(const mtts_hifigan* h, int B, int T) {
     C /= 2;
     if (L * C > big) big = L * C;
   }
-  const int64_t tcb = h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0;   // + halo rows
+  const int64_t tcb = h->engine >= 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0;   // + halo rows
   return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + 2 * (tcb / 4 + 64);
 }
 
@@ -624,14 +624,15 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
   float* mp = ar.take<float>((int64_t)B * Tp * h->in_channels);
   float* bufs[5];
   for (int i = 0; i < 5; ++i) bufs[i] = ar.take<float>((int64_t)B * big);
-  ConvTc tc{h->engine, nullptr, h->engine == 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0};
+  ConvTc tc{h->engine, nullptr, h->engine >= 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0};
   char* planes2 = nullptr;                      // second plane buffer for the fused ResBlock flow
   if (tc.bytes) {
     tc.scratch = ar.take<char>(tc.bytes);
     planes2 = ar.take<char>(tc.bytes);
   }
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "hifigan", ar.off);
-  bool fused = h->engine == 1 && tc.scratch && planes2;
+  bool fused = h->engine >= 1 && tc.scratch && planes2;
+  const int hfmt = tc_fmt_of_engine(h->engine);
   for (int n = 0; fused && n < h->n_ups * h->n_kernels; ++n)
     for (int m = 0; m < 3; ++m) fused = fused && h->resblocks[n].w1_tc[m] && h->resblocks[n].w2_tc[m];
   // replicate-pad `pad` frames at both ends (HifiganGenerator.inference)
@@ -678,7 +679,7 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
           const int h1 = rb.dil[m] * (rb.k - 1) / 2;
           mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], nullptr, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);
           c1.pre_act = MTTS_ACT_LEAKY; c1.pre_slope = 0.1f;
-          c1.w_tc = rb.w1_tc[m]; c1.tc_scratch = tc.scratch; c1.tc_scratch_bytes = tc.bytes;
+          c1.w_tc = rb.w1_tc[m]; c1.tc_scratch = tc.scratch; c1.tc_scratch_bytes = tc.bytes; c1.tc_fmt = hfmt;
           c1.tc_presplit = (m > 0);              // m == 0: split_pad(leaky(oup)) runs inside conv_tc
           c1.y = nullptr;
           c1.tc_out_planes = reinterpret_cast<void*>((((uintptr_t)planes2) + 1023) & ~(uintptr_t)1023);
@@ -690,7 +691,7 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
           MTTS_TRY(halo_fill(planes2, B, Lo, Co, h2, h2, MTTS_PAD_REFLECT, st));
           const bool lastm = (m == 2);
           mtts_conv_params c2 = conv_same_params(nullptr, rb.w2[m], rb.b2[m], lastm ? z : xr, B, Lo, Co, Co, rb.k, 1, MTTS_PAD_REFLECT);
-          c2.w_tc = rb.w2_tc[m]; c2.tc_scratch = planes2; c2.tc_scratch_bytes = tc.bytes; c2.tc_presplit = 1;
+          c2.w_tc = rb.w2_tc[m]; c2.tc_scratch = planes2; c2.tc_scratch_bytes = tc.bytes; c2.tc_presplit = 1; c2.tc_fmt = hfmt;
           c2.res = xcur; c2.res_batch_stride = (int64_t)Lo * Co; c2.ldr = Co;
           if (lastm) {
             c2.out_scale = 1.0f / (float)h->n_kernels;
@@ -797,7 +798,7 @@ int mtts_encoder_forward_f32(const mtts_encoder* enc, const float* x, float* y, 
                              int64_t workspace_bytes, void* stream) {
   MTTS_REQUIRE(enc && enc->layers && x && y && workspace, "null pointer");
   Arena ar(workspace, workspace_bytes);
-  TcScratch tcs{nullptr, tc_scratch_bytes(enc, (int64_t)B * T), (int64_t)B * T};
+  TcScratch tcs{nullptr, tc_scratch_bytes(enc, (int64_t)B * T), (int64_t)B * T, tc_fmt_of_engine(enc->engine)};
   if (tcs.bytes) tcs.p = ar.take<char>(tcs.bytes);
   return encoder_forward(enc, x, y, B, T, mask, mask_sb, mask_sh, mask_sq, last_row_only, ar, &tcs,
                          (cudaStream_t)stream);
@@ -807,10 +808,14 @@ int64_t mtts_linear_tc_scratch_bytes(int64_t rows_cap, int32_t K) { return linea
 int mtts_linear_tc_f32(const float* x, int32_t ldx, int64_t M, int32_t K, const void* w_planes, int32_t N,
                        const float* bias, const float* res, int32_t ldr, float* y, int32_t ldy, int32_t pre_act,
                        float pre_slope, int32_t post_act, void* scratch, int64_t scratch_bytes, int64_t rows_cap,
-                       void* stream) {
+                       int32_t fmt, void* stream) {
   return linear_tc(x, ldx, M, K, w_planes, N, bias, res, ldr, y, ldy, pre_act, pre_slope, post_act, 1.0f, scratch,
-                   scratch_bytes, rows_cap, (cudaStream_t)stream);
+                   scratch_bytes, rows_cap, fmt, (cudaStream_t)stream);
 }
+int mtts_split_planes_f32(const float* x, int32_t ldx, int64_t rows, int32_t C, void* planes, int32_t fmt, void* stream) {
+  return split_planes(x, ldx, rows, C, planes, fmt, (cudaStream_t)stream);
+}
+int mtts_tc_overflow_bind(int32_t* flag_dev) { return tc_overflow_bind(flag_dev); }
 
 int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) { return plm_ws_floats(m, B, T) * 4 + 8192; }
 int mtts_plm_infer_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,

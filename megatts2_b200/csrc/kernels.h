@@ -1,21 +1,58 @@
 // Internal (C++) entry points shared by the drivers and the C ABI.
 #pragma once
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "common.cuh"
 
 namespace mtts {
-// optional bf16x3 plane output of a producer kernel (feeds the tensor-core engine without a split pass)
+// Tensor-core operand formats ("planes": 2-byte elements in the activation's own (B, Tp, C) layout):
+//   fmt 0  bf16x3: x = p0 + p1 + p2 (three bf16 terms, to ~2^-24); six MMAs per product
+//   fmt 1  f16x2 : x = p0 + p1 * 2^-11 (two fp16 terms, the residual stored SCALED by 2^11 so it keeps the
+//                  magnitude - and the normal range - of x; 22 significant bits); three MMAs per product
+//                  (x0w0 | x0w1' + x1'w0, the second accumulator scaled by 2^-11 in the epilogue).  fp16 range:
+//                  |x| > 65504 cannot be represented - the split then poisons the value (inf/NaN propagate to the
+//                  output) and raises the caller-registered overflow flag (mtts_tc_overflow_bind).
+enum { MTTS_TC_BF16X3 = 0, MTTS_TC_F16X2 = 1 };
+constexpr float F16X2_SCALE = 2048.0f;           // 2^11
+constexpr float F16X2_INV_SCALE = 1.0f / 2048.0f;
+
+// optional plane output of a producer kernel (feeds the tensor-core engine without a split pass)
 struct PlanesOut {
-  __nv_bfloat16* p;      // plane 0; planes 1, 2 follow at +stride, +2*stride (elements)
+  __nv_bfloat16* p;      // plane 0; planes 1 (, 2) follow at +stride (, +2*stride) elements; 2-byte elements of `fmt`
   int64_t stride;
   int ld;                // row stride (elements)
   int act;               // activation applied to the planes copy (the consumer's pre-activation)
   float slope;
+  int fmt;               // MTTS_TC_BF16X3 | MTTS_TC_F16X2
+  int32_t* ovf;          // f16x2 range flag (device, may be null)
 };
 
-// x = p0 + p1 + p2 to ~2^-24 (round-to-nearest at every step); 4 consecutive elements -> one 8-byte store per plane
-__device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t plane_stride, int64_t off, const float* v) {
+// 4 consecutive elements -> one 8-byte store per plane
+__device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t plane_stride, int64_t off, const float* v,
+                                              int fmt = MTTS_TC_BF16X3, int32_t* ovf = nullptr) {
+  if (fmt == MTTS_TC_F16X2) {
+    uint16_t h[2][4];
+    bool bad = false;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const __half x1 = __float2half_rn(v[e]);                       // +-inf beyond the fp16 range
+      const __half x2 = __float2half_rn((v[e] - __half2float(x1)) * F16X2_SCALE);   // exact difference, exact scaling
+      h[0][e] = __half_as_ushort(x1);
+      h[1][e] = __half_as_ushort(x2);
+      bad |= !(fabsf(v[e]) <= 65504.0f);                             // also NaN
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      uint2 o;
+      o.x = (uint32_t)h[q][0] | ((uint32_t)h[q][1] << 16);
+      o.y = (uint32_t)h[q][2] | ((uint32_t)h[q][3] << 16);
+      *reinterpret_cast<uint2*>(planes + q * plane_stride + off) = o;
+    }
+    if (bad && ovf) *ovf = 1;
+    return;
+  }
+  // bf16x3: round-to-nearest at every step
   __nv_bfloat16 p[3][4];
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
@@ -34,6 +71,11 @@ __device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t pla
     *reinterpret_cast<uint2*>(planes + q * plane_stride + off) = o;
   }
 }
+// the overflow flag registered for the current device (null if none) and the current device's id / SM count
+int32_t* tc_ovf_ptr();
+int cur_device();
+int cur_device_sms();
+static inline int tc_fmt_of_engine(int engine) { return engine == 2 ? MTTS_TC_F16X2 : MTTS_TC_BF16X3; }
 int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
                  int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, PlanesOut po, cudaStream_t st);
 int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
@@ -44,7 +86,10 @@ int halo_fill(void* planes_base, int B, int T, int C, int hl, int hr, int pad_mo
 int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K);
 int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,
               const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,
-              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, cudaStream_t st);
+              float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, int fmt, cudaStream_t st);
+int split_planes(const float* x, int ldx, int64_t rows, int C, void* planes, int fmt, cudaStream_t st);
+int tc_overflow_bind(int32_t* flag);
+int mask_tail(float* x, int B, int rows, int L, const int32_t* keep, cudaStream_t st);
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
               int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, cudaStream_t st);
 int attention(const mtts_attn_params& p, cudaStream_t st);

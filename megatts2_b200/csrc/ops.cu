@@ -66,7 +66,7 @@ layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const
       if (po.p) {
 #pragma unroll
         for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], po.act, po.slope);
-        store_planes4(po.p, po.stride, row * po.ld + c, o);
+        store_planes4(po.p, po.stride, row * po.ld + c, o, po.fmt, po.ovf);
       }
     }
   } else {
@@ -128,7 +128,7 @@ layernorm_reg_kernel(const float* x, int ldx, const float* __restrict__ gamma, c
     if (po.p) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], po.act, po.slope);
-      store_planes4(po.p, po.stride, row * po.ld + c, o);
+      store_planes4(po.p, po.stride, row * po.ld + c, o, po.fmt, po.ovf);
     }
   }
 }
@@ -141,6 +141,7 @@ int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta,
   MTTS_REQUIRE(x && gamma && beta && (y || po.p), "null pointer");
   MTTS_REQUIRE(C > 0 && ldx >= C && (!y || ldy >= C), "bad dims");
   MTTS_REQUIRE(!(accumulate && !y), "accumulate needs a y buffer");
+  MTTS_REQUIRE(post_act != MTTS_ACT_LEAKY, "leaky post-activation is not supported by LayerNorm (no slope argument)");
   if (rows <= 0) return 0;
   const int vec = (C % 4 == 0) && (ldx % 4 == 0) && (!y || ((ldy % 4 == 0) && al16(y))) && al16(x) && al16(gamma) &&
                   al16(beta) && (!res || ((ldr % 4 == 0) && al16(res)));
@@ -166,7 +167,7 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
               float* y, int ldy, int64_t rows, int C, float eps, int post_act, int accumulate,
               cudaStream_t st) {
   MTTS_REQUIRE(y, "null pointer");
-  PlanesOut po{nullptr, 0, 0, 0, 0.f};
+  PlanesOut po{nullptr, 0, 0, 0, 0.f, 0, nullptr};
   return layernorm_ex(x, ldx, gamma, beta, res, ldr, y, ldy, rows, C, eps, post_act, accumulate, po, st);
 }
 
@@ -178,7 +179,7 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
 // cross-attention, Tk ~ 32).  For dh <= 128 a CTA covers 64 query rows, i.e. a whole AR-step sequence:
 // K and V are read once per (b, h).
 template <int NI, int RW, int NW, int KPL>
-__global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p, const int vec) {
+__global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p, const int vec, int32_t* ovf) {
   constexpr int DH = 32 * NI;
   constexpr int BQ = RW * NW, BKV = 32 * KPL, NT = NW * 32;
   extern __shared__ __align__(16) float sm[];
@@ -351,7 +352,7 @@ __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p,
       if (qr >= p.Tq) continue;
       const float4 v = *reinterpret_cast<const float4*>(stg + i * DH + d);
       const float vv[4] = {v.x, v.y, v.z, v.w};
-      store_planes4(pl, p.o_plane_stride, ((int64_t)b * p.Tq + qr) * p.o_planes_ld + (int64_t)h * DH + d, vv);
+      store_planes4(pl, p.o_plane_stride, ((int64_t)b * p.Tq + qr) * p.o_planes_ld + (int64_t)h * DH + d, vv, p.o_planes_fmt, ovf);
     }
   }
 }
@@ -361,17 +362,19 @@ static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   constexpr int DH = 32 * NI;
   constexpr int BQ = RW * NW, BKV = 32 * KPL;
   const size_t smem = sizeof(float) * (BQ * DH + BKV * (DH + 4) + BKV * DH + NW * RW * BKV);
-  static bool configured = false;   // per-process, per-instantiation; attribute set is idempotent
-  if (!configured) {
+  // the max-dynamic-shared-memory attribute is per device: one flag per (instantiation, device)
+  static std::atomic<uint64_t> configured{0};
+  const int dev = cur_device();
+  if (!(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
     cudaError_t e = cudaFuncSetAttribute(attn_kernel<NI, RW, NW, KPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "attention", (long long)e);
-    configured = true;
+    configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   auto al = [](const void* q) { return (((uintptr_t)q) & 15) == 0; };
   const int vec = al(p.q) && al(p.k) && al(p.v) && p.q_st % 4 == 0 && p.k_st % 4 == 0 && p.v_st % 4 == 0 &&
                   p.q_sb % 4 == 0 && p.k_sb % 4 == 0 && p.v_sb % 4 == 0;
   dim3 grid((unsigned)cdiv64(p.Tq, BQ), (unsigned)p.H, (unsigned)p.B);
-  attn_kernel<NI, RW, NW, KPL><<<grid, NW * 32, smem, st>>>(p, vec);
+  attn_kernel<NI, RW, NW, KPL><<<grid, NW * 32, smem, st>>>(p, vec, p.o_planes ? tc_ovf_ptr() : nullptr);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -681,6 +684,22 @@ int copy_strided(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc, float
   MTTS_REQUIRE(B <= 65535 && cdiv64(C, 32) <= 65535, "grid too large");
   dim3 grid((unsigned)cdiv64(T + 2 * pad_rep, 32), (unsigned)cdiv64(C, 32), (unsigned)B);
   copy_strided_kernel<<<grid, 256, 0, st>>>(x, x_sb, x_st, x_sc, y, y_sb, y_st, y_sc, T, C, pad_rep);
+  MTTS_CHECK_LAUNCH();
+  return 0;
+}
+
+__global__ void mask_tail_kernel(float* __restrict__ x, int rows, int L, const int32_t* __restrict__ keep) {
+  const int b = blockIdx.z, r = blockIdx.y;
+  const int k0 = max(keep[b], 0);
+  float* xr = x + ((int64_t)b * rows + r) * L;
+  for (int i = k0 + blockIdx.x * blockDim.x + threadIdx.x; i < L; i += gridDim.x * blockDim.x) xr[i] = 0.f;
+}
+int mask_tail(float* x, int B, int rows, int L, const int32_t* keep, cudaStream_t st) {
+  MTTS_REQUIRE(x && keep && B >= 0 && rows >= 0 && L >= 0, "bad arguments");
+  if (B == 0 || rows == 0 || L == 0) return 0;
+  MTTS_REQUIRE(B <= 65535 && rows <= 65535, "grid too large");
+  dim3 grid((unsigned)(cdiv64(L, 1024) < 64 ? cdiv64(L, 1024) : 64), (unsigned)rows, (unsigned)B);
+  mask_tail_kernel<<<grid, 256, 0, st>>>(x, rows, L, keep);
   MTTS_CHECK_LAUNCH();
   return 0;
 }

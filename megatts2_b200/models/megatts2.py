@@ -323,6 +323,7 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
             pl.sig = sig
             s = L.Hifigan()
             s.engine = engine
+            fmt = pack.engine_fmt(engine)
             s.in_channels, s.ch0 = c["in_channels"], c["upsample_initial_channel"]
             s.n_ups, s.n_kernels = len(c["upsample_factors"]), len(c["resblock_kernel_sizes"])
             s.inference_padding = c["inference_padding"]
@@ -331,9 +332,8 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
                 s.up_factor[i], s.up_kernel[i] = u, k
                 wp, bp = pack.pack_conv_transpose(self.ups[i].weight, self.ups[i].bias, u)
                 s.w_up[i], s.b_up[i] = pl.p(wp), pl.p(bp)
-                if engine == 1:     # (2, Cin, s*Cout) fp32 -> (3, 2, s*Cout, Cin) bf16 planes
-                    tup = pack.pack_tc_planes(wp.permute(0, 2, 1).reshape(-1, wp.shape[1])).reshape(
-                        3, 2, wp.shape[2], wp.shape[1]).contiguous()
+                if engine >= 1:     # (2, Cin, s*Cout) fp32 -> (3 | 2, 2, s*Cout, Cin) operand planes
+                    tup = pack.pack_conv_transpose_tc_planes(wp, fmt)
                     pl.keep.append(tup)
                     s.w_up_tc[i] = tup.data_ptr()
             arr = (L.HifiganResblock * len(self.resblocks))()
@@ -345,8 +345,8 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
                     arr[n].dil[m] = c["resblock_dilation_sizes"][j][m]
                     arr[n].w1[m], arr[n].b1[m] = pl.p(pack.pack_conv(rb.convs1[m].weight)), pl.p(rb.convs1[m].bias)
                     arr[n].w2[m], arr[n].b2[m] = pl.p(pack.pack_conv(rb.convs2[m].weight)), pl.p(rb.convs2[m].bias)
-                    if engine == 1:
-                        t1, t2 = pack.pack_conv_tc_planes(rb.convs1[m].weight), pack.pack_conv_tc_planes(rb.convs2[m].weight)
+                    if engine >= 1:
+                        t1, t2 = pack.pack_conv_tc_planes(rb.convs1[m].weight, fmt), pack.pack_conv_tc_planes(rb.convs2[m].weight, fmt)
                         pl.keep += [t1, t2]
                         arr[n].w1_tc[m], arr[n].w2_tc[m] = t1.data_ptr(), t2.data_ptr()
             pl.hold(arr)
@@ -382,29 +382,79 @@ class HifiganGenerator(pack.PlanMixin, nn.Module):
         return self.inference_cl(ops.to_channels_last(c))
 
 
+def convert_speechbrain_hifigan_state_dict(sd):
+    """speechbrain ``HifiganGenerator`` checkpoint keys -> this module's keys, folding weight norm.
+
+    speechbrain wraps every conv as ``<name>.conv`` and applies ``torch.nn.utils.weight_norm`` (dim 0), so a
+    ``generator.ckpt`` holds ``conv_pre.conv.weight_g / weight_v / bias``, ``ups.{i}.conv.*``,
+    ``resblocks.{n}.convs{1,2}.{m}.conv.*``, ``conv_post.conv.*`` (or, with the parametrization API,
+    ``...conv.parametrizations.weight.original0 / original1``) [published layout, restated from memory: speechbrain is
+    not vendored by the reference - SURVEY.md 8c].  Folded weight: ``w = g * v / ||v||`` with the norm over every dim but 0
+    (what ``remove_weight_norm`` leaves behind, which ``HIFIGAN.decode_batch`` calls before its first inference).  Keys
+    that are already in this module's layout pass through."""
+    out, groups = {}, {}
+    for k, v in sd.items():
+        k2 = k[len("generator."):] if k.startswith("generator.") else k
+        k2 = k2.replace(".conv.", ".")
+        for a, b in ((".parametrizations.weight.original0", ".weight_g"), (".parametrizations.weight.original1", ".weight_v")):
+            k2 = k2.replace(a, b)
+        if k2.endswith(".weight_g") or k2.endswith(".weight_v"):
+            groups.setdefault(k2[:-9], {})[k2[-1]] = v
+        else:
+            out[k2] = v
+    for base, gv in groups.items():
+        if set(gv) != {"g", "v"}:
+            raise L.MttsError(f"weight-norm pair incomplete for {base!r}")
+        v = gv["v"].float()
+        norm = v.reshape(v.shape[0], -1).norm(dim=1).reshape(-1, *([1] * (v.dim() - 1)))
+        out[base + ".weight"] = gv["g"].float().reshape_as(norm) * v / norm
+    return out
+
+
 class HIFIGAN(nn.Module):
     """speechbrain.pretrained.HIFIGAN call surface used by the reference
     (models/megatts2.py:321-323, 370-372): ``from_hparams(source=...)``, ``eval()``,
-    ``decode_batch(mel (B,80,T)) -> (B,1,samples)``.  There is no network here, so
-    ``from_hparams`` takes an explicit ``state_dict`` (weight-norm folded) or leaves the
-    generator at its constructor init."""
+    ``decode_batch(mel (B,80,T)) -> (B,1,samples)``.  There is no network here: ``source`` must be a local
+    directory holding ``generator.ckpt`` (the file speechbrain's hyperparams.yaml names) or a checkpoint file, or an
+    explicit ``state_dict`` must be given; anything else raises instead of silently returning a randomly
+    initialised vocoder."""
 
     def __init__(self, generator: HifiganGenerator = None):
         super().__init__()
         self.generator = generator if generator is not None else HifiganGenerator()
 
     @classmethod
-    def from_hparams(cls, source=None, state_dict=None, device=None, **kw):
+    def from_hparams(cls, source=None, state_dict=None, device=None, random_init=False, **kw):
+        import os
         m = cls()
+        if state_dict is None and source is not None:
+            path = os.path.join(source, "generator.ckpt") if os.path.isdir(source) else source
+            if os.path.isfile(path):
+                state_dict = torch.load(path, map_location="cpu")
+                if isinstance(state_dict, dict) and "state_dict" in state_dict:
+                    state_dict = state_dict["state_dict"]
         if state_dict is not None:
-            m.generator.load_state_dict(state_dict, strict=True)
+            m.generator.load_state_dict(convert_speechbrain_hifigan_state_dict(state_dict), strict=True)
+        elif not random_init:
+            raise L.MttsError(
+                f"HIFIGAN.from_hparams(source={source!r}): no local generator checkpoint found and no state_dict given "
+                "(this build cannot download speechbrain/tts-hifigan-libritts-16kHz); pass source=<dir with generator.ckpt>, "
+                "state_dict=..., or random_init=True for synthetic-weight benchmarks")
         if device is not None:
             m = m.to(device)
         return m.eval()
 
     def decode_batch(self, spectrogram: torch.Tensor, mel_lens=None, hop_len=None) -> torch.Tensor:
+        """mel (B,80,T) -> (B,1,256*(T+10)).  With ``mel_lens`` and ``hop_len`` the samples past
+        ``mel_lens[b] * hop_len`` are zeroed, like speechbrain's ``mask_noise`` [memory]."""
         dev = next(self.generator.parameters()).device
-        return self.generator.inference(spectrogram.to(dev))
+        wav = self.generator.inference(spectrogram.to(dev))
+        if (mel_lens is None) != (hop_len is None):
+            raise L.MttsError("decode_batch: give both mel_lens and hop_len, or neither")
+        if mel_lens is not None:
+            keep = (torch.as_tensor(mel_lens).to(torch.int64) * int(hop_len)).to(device=dev, dtype=torch.int32)
+            ops.mask_tail(wav, keep)
+        return wav
 
     def decode_batch_cl(self, mel_cl: torch.Tensor) -> torch.Tensor:
         return self.generator.inference_cl(mel_cl)
@@ -433,25 +483,89 @@ class Megatts(nn.Module):
 
     @torch.no_grad()
     def synthesize(self, phone_tokens: torch.Tensor, mels: torch.Tensor, forced_durations: torch.Tensor = None,
-                   return_intermediates: bool = False, causal_decode: bool = False):
-        """phone_tokens (B,Tp) int64, mels (B,Tm,80) prompt mel (frames-major) -> wav (B,1,256*(sum d + 10)).
-        Steps = models/megatts2.py:354-370.  ``forced_durations`` (B,Tp) int32 replaces the ADM output
-        for shape control (the ADM still runs).  ``causal_decode=True`` swaps both AR loops for the opt-in causal
-        KV-cache decode (training semantics; NOT the reference's infer() - different ids)."""
+                   return_intermediates: bool = False, causal_decode: bool = False, prompt_mels: torch.Tensor = None,
+                   return_lengths: bool = False, check_range: bool = True):
+        """phone_tokens (B,Tp) int64, mels (B,Tm,80) prompt mel (frames-major) -> wav (B,1,256*(max sum d + 10)).
+        Steps = models/megatts2.py:354-373; every utterance's result equals the reference's batch-1 run on it
+        (utterances are independent; the only cross-utterance coupling would be the zero rows the LengthRegulator
+        appends to shorter utterances, which the mel decoder and the vocoder must not see - so those two stages run
+        per group of equal sum(d), each group one launch sequence, results scattered back; with equal totals - the
+        benchmark's forced durations - that is a single group).  All utterances of a call share Tp and Tm (tensors are
+        rectangular; ``synthesize_many`` buckets ragged inputs).
+
+        ``forced_durations`` (B,Tp) int32 replaces the ADM output for shape control (the ADM still runs).
+        ``prompt_mels`` (B,Tq,80): re-vocode the prompt and prepend it, as the reference does (:371-373).
+        ``return_lengths``: also return the valid sample count per utterance (prompt part included).
+        ``causal_decode=True`` swaps both AR loops for the opt-in causal KV-cache decode (training semantics; NOT the
+        reference's infer() - different ids).
+        ``check_range``: with the f16x2 operand engine, read the range flag after the batch (one 4-byte readback) and,
+        if any activation left the fp16 range, redo the batch on the bf16x3 engine."""
+        dev = phone_tokens.device
+        out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels)
+        if check_range and pack.default_engine() == pack.ENGINE_F16X2 and ops.tc_overflow(dev):
+            import warnings
+            warnings.warn("megatts2_b200: an activation left the fp16 range of the f16x2 operand split; "
+                          "re-running this batch on the bf16x3 engine")
+            with pack.engine_scope(pack.ENGINE_BF16X3):
+                out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels)
+        if return_intermediates:
+            return out
+        return (out["wav"], out["wav_lens"]) if return_lengths else out["wav"]
+
+    def _synthesize(self, phone_tokens, mels, forced_durations, causal_decode, prompt_mels):
         tc_latent = self.generator.mrte.tc_latent(phone_tokens, mels)
         adm_decode = self.adm.infer_causal if causal_decode else self.adm.infer
         plm_decode = self.plm.infer_causal if causal_decode else self.plm.infer
         dt = adm_decode(tc_latent)[..., 0]
         d_used = dt if forced_durations is None else forced_durations.to(dt.device, torch.int32)
-        tc_expand = self.lr(tc_latent, d_used)                    # one host sync for the output length
+        tc_expand, totals = ops.length_regulate(tc_latent, d_used, return_host_totals=True)   # one host sync
         tc8 = ops.maxpool_time(tc_expand, 8)
         p_codes = plm_decode(tc8)
-        mel = self.generator.decode_mel_cl(tc_expand, p_codes)    # (B, L, 80) channels-last
-        wav = self.hifi_gan.decode_batch_cl(mel)
-        if return_intermediates:
-            return dict(tc_latent=tc_latent, dt=dt, tc_latent_expand=tc_expand, tc8=tc8, p_codes=p_codes,
-                        mel=mel, wav=wav)
-        return wav
+        B, Lmax = tc_expand.shape[0], tc_expand.shape[1]
+        hop = HIFIGAN_HOP_LENGTH
+        pad = self.hifi_gan.generator.cfg["inference_padding"]
+        if all(t == Lmax for t in totals):
+            mel = self.generator.decode_mel_cl(tc_expand, p_codes)    # (B, L, 80) channels-last
+            wav = self.hifi_gan.decode_batch_cl(mel)
+        else:
+            # ragged totals: decoder + vocoder per group of equal length (exactly the reference's batch-1 results)
+            mel = torch.zeros(B, Lmax, self.generator.mrte.mel_bins, dtype=torch.float32, device=tc_expand.device)
+            wav = torch.zeros(B, 1, hop * (Lmax + 2 * pad), dtype=torch.float32, device=tc_expand.device)
+            for Lg in sorted(set(totals)):
+                idx = torch.tensor([i for i, t in enumerate(totals) if t == Lg], device=tc_expand.device)
+                if Lg == 0:
+                    continue
+                mg = self.generator.decode_mel_cl(tc_expand[idx, :Lg].contiguous(), p_codes[idx, :(Lg + 7) // 8].contiguous())
+                wg = self.hifi_gan.decode_batch_cl(mg)
+                mel[idx, :Lg] = mg
+                wav[idx, :, :wg.shape[-1]] = wg
+        wav_lens = [hop * (t + 2 * pad) for t in totals]
+        if prompt_mels is not None:
+            pw = self.hifi_gan.decode_batch_cl(prompt_mels)           # (B, 1, hop*(Tq + 2 pad))   (:371-372)
+            wav = torch.cat([pw, wav], dim=-1)                        # (:373)
+            wav_lens = [n + pw.shape[-1] for n in wav_lens]
+        return dict(tc_latent=tc_latent, dt=dt, tc_latent_expand=tc_expand, tc8=tc8, p_codes=p_codes,
+                    mel=mel, wav=wav, totals=totals, wav_lens=wav_lens)
+
+    @torch.no_grad()
+    def synthesize_many(self, items, max_batch: int = 64, **kw):
+        """Ragged front door: ``items`` = list of (phone (Tp_i,) int64, prompt mel (Tm_i, 80)).  Utterances are
+        bucketed by (Tp, Tm) - the MRTE phone encoder and the prompt encoder are unmasked in the reference
+        (modules/mrte.py:154-171), so padding either would change results - and each bucket runs as one batch.
+        Returns a list of 1-D waveforms (valid samples only), in input order."""
+        buckets = {}
+        for i, (ph, m) in enumerate(items):
+            buckets.setdefault((ph.shape[0], m.shape[0]), []).append(i)
+        out = [None] * len(items)
+        for _, ids in sorted(buckets.items()):
+            for s in range(0, len(ids), max_batch):
+                chunk = ids[s:s + max_batch]
+                ph = torch.stack([items[i][0] for i in chunk])
+                mm = torch.stack([items[i][1] for i in chunk])
+                wav, lens = self.synthesize(ph, mm, return_lengths=True, **kw)
+                for j, i in enumerate(chunk):
+                    out[i] = wav[j, 0, :lens[j]]
+        return out
 
     def forward(self, wavs_dir: str, text: str):
         """Reference signature (models/megatts2.py:325-375): prompt wavs + text -> writes test.wav."""
@@ -473,7 +587,5 @@ class Megatts(nn.Module):
         mels = torch.cat(mels, 0).unsqueeze(0)
         tt, ttc = TextTokenizer(), TokensCollector(self.symbol_table)
         phone_tokens = ttc.phone2token(tt.tokenize_lty(tt.tokenize(text))).unsqueeze(0).to(dev)
-        audio = self.synthesize(phone_tokens, mels)
-        audio_prompt = self.hifi_gan.decode_batch_cl(mels_prompt.unsqueeze(0))
-        audio = torch.cat([audio_prompt, audio], dim=-1)
+        audio = self.synthesize(phone_tokens, mels, prompt_mels=mels_prompt.unsqueeze(0))
         torchaudio.save('test.wav', audio[0].cpu(), HIFIGAN_SR)

@@ -47,10 +47,10 @@ class MultiHeadAttention(pack.PlanMixin, nn.Module):
             pl = pack.Plan()
             pl.sig = sig
             pl.wq = pack.pack_linear(self.w_q.weight)
-            pl.wkv = pack.pack_linear(torch.cat([self.w_k.weight.detach(), self.w_v.weight.detach()], 0))
-            pl.bkv = torch.cat([self.w_k.bias.detach(), self.w_v.bias.detach()]).contiguous()
+            pl.wkv = pack.pack_linear(pack.cat_rows(self.w_k.weight, self.w_v.weight))
+            pl.bkv = pack.cat_vectors(self.w_k.bias, self.w_v.bias)
             pl.wqkv = pack.pack_qkv(self.w_q.weight, self.w_k.weight, self.w_v.weight)
-            pl.bqkv = torch.cat([self.w_q.bias.detach(), pl.bkv]).contiguous()
+            pl.bqkv = pack.cat_vectors(self.w_q.bias, self.w_k.bias, self.w_v.bias)
             pl.wo = pack.pack_linear(self.out_proj[0].weight)
             self._plan = pl
         return self._plan

@@ -50,7 +50,8 @@ def conv1d(x, w_packed, bias=None, *, k, stride=1, dil=1, pad=0, pad_mode=L.PAD_
            pre_slope=0.0, post_act=L.ACT_NONE, post_slope=0.0, res=None, out=None, out_scale=1.0, accumulate=False,
            t_out=None, in_lens=None, w_tc=None):
     """x (B,T,Cin) channels-last, w_packed (k,Cin,Cout) -> (B,T_out,Cout).
-    w_tc: optional (3,k,Cout,Cin) bf16 planes -> the tcgen05 engine is used when the shape is eligible."""
+    w_tc: optional operand planes, (3,k,Cout,Cin) bf16 [bf16x3] or (2,k,Cout,Cin) fp16 [f16x2] -> the tcgen05 engine
+    is used when the shape is eligible."""
     x = _dev(x, name="x")
     x, x_sb, ldx = _rows(x)
     B, Tin, Cin = x.shape
@@ -76,10 +77,12 @@ def conv1d(x, w_packed, bias=None, *, k, stride=1, dil=1, pad=0, pad_mode=L.PAD_
     p.out_scale, p.accumulate = out_scale, int(accumulate)
     p.in_lens = _dev(in_lens, torch.int32, "in_lens").data_ptr() if in_lens is not None else None
     if w_tc is not None:
-        assert w_tc.dtype == torch.bfloat16 and w_tc.is_contiguous() and tuple(w_tc.shape) == (3, k, Cout, Cin)
+        fmt = _plane_fmt(w_tc)
+        assert w_tc.is_contiguous() and tuple(w_tc.shape) == (3 - fmt, k, Cout, Cin)
         nbytes = 6 * B * (t_out + dil * (k - 1)) * Cin + 4096
         scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
-        p.w_tc, p.tc_scratch, p.tc_scratch_bytes = w_tc.data_ptr(), scratch.data_ptr(), nbytes
+        p.w_tc, p.tc_scratch, p.tc_scratch_bytes, p.tc_fmt = w_tc.data_ptr(), scratch.data_ptr(), nbytes, fmt
+        tc_overflow_bind(x.device)
     L.check(L.lib().mtts_conv1d_f32(C.byref(p), _stream()))
     return out
 
@@ -91,16 +94,27 @@ def linear(x, w_packed, bias=None, **kw):
     return y.reshape(*shp[:-1], w_packed.shape[2])
 
 
+def _plane_fmt(w_planes):
+    if w_planes.dtype == torch.float16:
+        return L.TC_F16X2
+    if w_planes.dtype == torch.bfloat16:
+        return L.TC_BF16X3
+    raise L.MttsError(f"operand planes must be bf16 (bf16x3) or fp16 (f16x2), got {w_planes.dtype}")
+
+
 def linear_tc(x, w_planes, bias=None, *, res=None, pre_act=L.ACT_NONE, pre_slope=0.0, post_act=L.ACT_NONE):
-    """Tensor-core (tcgen05, bf16x3) dense layer: x (..., K) fp32, w_planes (3, N, K) bf16 -> (..., N) fp32."""
+    """Tensor-core (tcgen05) dense layer: x (..., K) fp32, w_planes (3, N, K) bf16 [bf16x3] or (2, N, K) fp16 [f16x2]
+    -> (..., N) fp32."""
     x = _dev(x, name="x")
     shp = x.shape
     x2 = x.reshape(-1, shp[-1])
     if x2.stride(1) != 1 or x2.stride(0) % 4 != 0 or x2.data_ptr() % 16 != 0:
         x2 = x2.contiguous()
     M, K = x2.shape
-    _, N, K2 = w_planes.shape
-    assert K2 == K and w_planes.dtype == torch.bfloat16 and w_planes.is_contiguous()
+    fmt = _plane_fmt(w_planes)
+    npl, N, K2 = w_planes.shape
+    assert K2 == K and npl == 3 - fmt and w_planes.is_contiguous()
+    tc_overflow_bind(x.device)
     y = torch.empty(M, N, dtype=_F32, device=x.device)
     r2 = res.reshape(M, N) if res is not None else None
     lib = L.lib()
@@ -108,7 +122,7 @@ def linear_tc(x, w_planes, bias=None, *, res=None, pre_act=L.ACT_NONE, pre_slope
     scratch = torch.empty(nbytes, dtype=torch.uint8, device=x.device)
     L.check(lib.mtts_linear_tc_f32(_ptr(x2), x2.stride(0), M, K, _ptr(w_planes), N, _ptr(bias), _ptr(r2),
                                    r2.stride(0) if r2 is not None else 0, _ptr(y), N, pre_act, pre_slope, post_act,
-                                   _ptr(scratch), nbytes, M, _stream()))
+                                   _ptr(scratch), nbytes, M, fmt, _stream()))
     return y.reshape(*shp[:-1], N)
 
 
@@ -220,9 +234,9 @@ def add_pe(x, pe, alpha=1.0):
     return y
 
 
-def length_regulate(x, dur, l_out=None):
-    """x (B,Tp,D), dur (B,Tp) int32 -> (B, l_out, D), totals (B,) int32.
-    l_out=None reads max(sum(dur)) back to the host (one sync, like the reference's .numpy())."""
+def length_regulate(x, dur, l_out=None, return_host_totals=False):
+    """x (B,Tp,D), dur (B,Tp) int32 -> (B, l_out, D), totals (B,) int32 (a host list with return_host_totals).
+    l_out=None reads sum(dur) per utterance back to the host (one sync, like the reference's .numpy())."""
     x, x_sb, ldx = _rows(_dev(x, name="x"))
     dur = _dev(dur, torch.int32, "dur").contiguous()
     B, Tp, D = x.shape
@@ -230,11 +244,27 @@ def length_regulate(x, dur, l_out=None):
     if l_out is None:
         L.check(L.lib().mtts_length_regulate_f32(_ptr(x), x_sb, ldx, _ptr(dur), Tp, B, Tp, D, 0, None, 0, D,
                                                  _ptr(totals), _stream()))
-        l_out = int(totals.max().item())
+        host_totals = totals.tolist()                 # B ints: the one host sync of the synthesis body
+        l_out = max(host_totals) if host_totals else 0
+    elif return_host_totals:
+        host_totals = None
     y = torch.empty(B, l_out, D, dtype=_F32, device=x.device)
     L.check(L.lib().mtts_length_regulate_f32(_ptr(x), x_sb, ldx, _ptr(dur), Tp, B, Tp, D, l_out, _ptr(y),
                                              y.stride(0), y.stride(1) if l_out > 0 else D, _ptr(totals), _stream()))
+    if return_host_totals:
+        return y, (host_totals if host_totals is not None else totals.tolist())
     return y, totals
+
+
+def mask_tail(x, keep):
+    """x (B, ..., L) contiguous fp32, keep (B,) int32: zero x[b, ..., keep[b]:] in place (speechbrain mask_noise)."""
+    x = _dev(x, name="x")
+    assert x.is_contiguous()
+    keep = _dev(keep, torch.int32, "keep").contiguous()
+    B, Lx = x.shape[0], x.shape[-1]
+    rows = x.numel() // max(B * Lx, 1)
+    L.check(L.lib().mtts_mask_tail_f32(_ptr(x), B, rows, Lx, _ptr(keep), _stream()))
+    return x
 
 
 def to_channels_last(x_bct, pad_rep=0):
@@ -285,18 +315,52 @@ def mel_spectrogram(wav, window, fb_w, fb_off, fb_start, n_mels=80, clamp=1e-5, 
     return out
 
 
+# ------------------------------------------------------------------------------ f16x2 range guard
+_ovf_flags = {}
+
+
+def _dev_index(device):
+    return torch.cuda.current_device() if device.index is None else device.index
+
+
+def tc_overflow_bind(device):
+    """Registers (once per device) the int32 flag the f16x2 operand split raises when an activation leaves the
+    fp16 range (|x| > 65504); returns the flag tensor."""
+    idx = _dev_index(device)
+    flag = _ovf_flags.get(idx)
+    if flag is None:
+        with torch.cuda.device(idx):
+            flag = torch.zeros(1, dtype=torch.int32, device=torch.device("cuda", idx))
+            L.check(L.lib().mtts_tc_overflow_bind(_ptr(flag)))
+        _ovf_flags[idx] = flag
+    return flag
+
+
+def tc_overflow(device, reset=True):
+    """True if any f16x2 split on `device` saw an out-of-range activation since the last reset (one host sync)."""
+    flag = tc_overflow_bind(device)
+    hit = bool(flag.item())
+    if hit and reset:
+        flag.zero_()
+    return hit
+
+
 # ------------------------------------------------------------------------------ workspace
 _ws_cache = {}
 
 
 def workspace(nbytes, device):
-    """A per-device scratch buffer that only grows (torch caching allocator underneath)."""
-    key = (device.type, device.index)
+    """A scratch buffer per (device, stream) that only grows (torch caching allocator underneath); the base address
+    is 256-byte aligned (the allocator's granularity is 512 bytes), which the C side's float4 / TMA carving relies on.
+    Work on different streams never shares scratch."""
+    tc_overflow_bind(device)
+    key = (device.type, _dev_index(device), torch.cuda.current_stream(device).cuda_stream)
     buf = _ws_cache.get(key)
     if buf is None or buf.numel() < nbytes:
         buf = None
         _ws_cache.pop(key, None)
         buf = torch.empty(int(nbytes) + 256, dtype=torch.uint8, device=device)
+        assert buf.data_ptr() % 256 == 0
         _ws_cache[key] = buf
     return buf
 

@@ -46,3 +46,13 @@ def build_megatts(wg, wp, wa, wh, device="cuda"):
     from megatts2_b200.models.megatts2 import Megatts
     return Megatts(generator=build_g(wg, device), plm=build_plm(wp, device), adm=build_adm(wa, device),
                    hifi_gan=build_hifigan(wh, device), device=device)
+
+
+def record(name, payload):
+    """Append a measured parity figure to gpurun_out/parity_rates.jsonl (the GPU box merges gpurun_out/ back; the
+    summary that is committed lives in profiles/)."""
+    import json
+    d = os.path.join(ROOT, "gpurun_out")
+    os.makedirs(d, exist_ok=True)
+    with open(os.path.join(d, "parity_rates.jsonl"), "a") as f:
+        f.write(json.dumps({"name": name, **payload}) + "\n")

@@ -23,13 +23,13 @@ def test_library_exports_every_declared_symbol():
     from megatts2_b200 import _lib as L
     lib = L.lib()
     syms = _header_symbols()
-    assert len(syms) == 39
+    assert len(syms) >= 42
     raw = ctypes.CDLL(L.LIB_PATH)
     for s in syms:
         assert hasattr(raw, s), f"missing export {s}"
         assert s in L.SIGNATURES, f"{s} has no ctypes signature"
     assert set(L.SIGNATURES) == set(syms)
-    assert lib.mtts_abi_version() == 1
+    assert lib.mtts_abi_version() == L.ABI_VERSION == 2
     assert lib.mtts_launch_count() == 0
 
 
@@ -240,6 +240,56 @@ def test_bf16x3_weight_planes_are_fp32_exact():
     pc = pack.pack_conv_tc_planes(wc)                                                          # (3, k, Cout, Cin)
     assert pc.shape == (3, 5, 8, 16)
     assert torch.equal(pc[0, 2], wc[:, :, 2].to(torch.bfloat16))
+
+
+def test_f16x2_weight_planes_cover_22_bits():
+    """pack_tc_planes(fmt=f16x2): w = w1 + w2 * 2^-11 with both terms fp16; the residual is stored scaled by 2^11 so it
+    stays a NORMAL fp16 number whenever w is (no precision cliff for small weights).  22 significant bits: relative
+    error <= 2^-22 for every |w| in the fp16 normal range - below the rounding noise of an fp32 dot product."""
+    from megatts2_b200 import pack
+    g = torch.Generator().manual_seed(6)
+    w = torch.randn(96, 160, generator=g) * torch.logspace(-4, 4, 160)           # 1e-4 .. 1e4: inside the fp16 normal range
+    planes = pack.pack_tc_planes(w, pack.FMT_F16X2)
+    assert planes.shape == (2, 96, 160) and planes.dtype == torch.float16
+    back = planes[0].double() + planes[1].double() / 2048.0
+    rel = ((back - w.double()).abs() / w.double().abs().clamp_min(1e-30))
+    inside = w.abs() >= 2.0 ** -14
+    assert rel[inside].max().item() <= 2.0 ** -22, rel[inside].max().item()
+    assert (back - w.double()).abs()[~inside].max().item() <= 2.0 ** -36                      # subnormal heads: absolute bound
+    assert torch.isfinite(planes.float()).all()
+    assert (planes[1].float().abs() <= planes[0].float().abs() * 1.0001 + 2.0 ** -13).all()    # scaled residual <= |w|
+    wc = torch.randn(8, 16, 5, generator=g)
+    pc = pack.pack_conv_tc_planes(wc, pack.FMT_F16X2)                                           # (2, k, Cout, Cin)
+    assert pc.shape == (2, 5, 8, 16) and torch.equal(pc[0, 2], wc[:, :, 2].to(torch.float16))
+
+
+def test_speechbrain_hifigan_key_conversion_folds_weight_norm():
+    """convert_speechbrain_hifigan_state_dict: `.conv.` nesting stripped, weight_g / weight_v folded with the dim-0 norm
+    of torch.nn.utils.weight_norm; the result loads strict=True into HifiganGenerator."""
+    from megatts2_b200.models.megatts2 import HIFIGAN, HifiganGenerator, convert_speechbrain_hifigan_state_dict
+    from megatts2_b200 import _lib as L
+    gen = HifiganGenerator()
+    sb = {}
+    g = torch.Generator().manual_seed(3)
+    want = {}
+    for k, v in gen.state_dict().items():
+        base, leaf = k.rsplit(".", 1)
+        if leaf == "bias":
+            sb[f"{base}.conv.bias"] = v.clone()
+            want[k] = v.clone()
+            continue
+        vv = torch.randn(v.shape, generator=g)
+        gg = torch.rand(v.shape[0], *([1] * (v.dim() - 1)), generator=g) + 0.5
+        sb[f"{base}.conv.weight_v"], sb[f"{base}.conv.weight_g"] = vv, gg
+        # the fold torch.nn.utils.weight_norm itself defines
+        want[k] = torch._weight_norm(vv, gg, 0)
+    out = convert_speechbrain_hifigan_state_dict(sb)
+    assert set(out) == set(gen.state_dict())
+    for k in out:
+        assert torch.allclose(out[k], want[k], rtol=1e-6, atol=1e-7), k
+    gen.load_state_dict(out, strict=True)
+    with pytest.raises(L.MttsError, match="no local generator checkpoint"):
+        HIFIGAN.from_hparams(source="speechbrain/tts-hifigan-libritts-16kHz")
 
 
 def test_shard_bounds_properties_hypothesis():

@@ -1,4 +1,5 @@
-"""GPU: the tcgen05 bf16x3 engine against fp64 and against the exact FFMA engine / golden ids."""
+"""GPU: the tcgen05 engine (both operand formats: bf16x3 = engine 1, f16x2 = engine 2) against fp64 and against the
+exact FFMA engine / golden ids."""
 import math
 
 import pytest
@@ -9,6 +10,11 @@ from megatts2_b200 import pack
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 DEV = "cuda"
+ENGINES = [pytest.param(1, id="bf16x3"), pytest.param(2, id="f16x2")]
+
+
+def fmt_of(engine):
+    return pack.engine_fmt(engine)
 
 
 def gen(seed):
@@ -32,8 +38,9 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("c", CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_linear_tc_vs_fp64(c):
+def test_linear_tc_vs_fp64(c, engine):
     from megatts2_b200 import ops
     g = gen(c["M"] + c["K"] + c["N"])
     x = torch.randn(c["M"], c["K"], generator=g) * 2
@@ -47,7 +54,7 @@ def test_linear_tc_vs_fp64(c):
         ref = torch.relu(ref)
     if r is not None:
         ref = ref + r.double()
-    y = ops.linear_tc(x.to(DEV), pack.pack_tc_planes(w).to(DEV), b.to(DEV) if b is not None else None,
+    y = ops.linear_tc(x.to(DEV), pack.pack_tc_planes(w.to(DEV), fmt_of(engine)), b.to(DEV) if b is not None else None,
                       res=r.to(DEV) if r is not None else None, post_act=1 if c.get("relu") else 0)
     torch.cuda.synchronize()
     err = (y.cpu().double() - ref).abs().max().item()
@@ -67,10 +74,55 @@ def test_split_planes_are_exact():
     assert (p.sum(0) - w).abs().max().item() <= 2.0 ** -22 * w.abs().max().item()
 
 
-def test_plm_tc_engine_matches_golden_ids(golden, weights_cpu):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_device_packing_equals_host_packing(engine):
+    """Weights are re-laid out and split by the library's own kernels on the device (mtts_copy_strided_f32 +
+    mtts_split_planes_f32); the torch implementation in pack.py (CPU tensors) is the layout specification: bit-equal."""
+    fmt = fmt_of(engine)
+    g = gen(17)
+    w2, wc, wt = torch.randn(300, 136, generator=g), torch.randn(96, 64, 7, generator=g), torch.randn(64, 32, 16, generator=g)
+    bt = torch.randn(32, generator=g)
+    for host, dev in ((pack.pack_linear(w2), pack.pack_linear(w2.to(DEV))),
+                      (pack.pack_conv(wc), pack.pack_conv(wc.to(DEV))),
+                      (pack.pack_qkv(w2[:100], w2[100:200], w2[200:]), pack.pack_qkv(w2[:100].to(DEV), w2[100:200].to(DEV), w2[200:].to(DEV))),
+                      (pack.pack_tc_planes(w2, fmt), pack.pack_tc_planes(w2.to(DEV), fmt)),
+                      (pack.pack_conv_tc_planes(wc, fmt), pack.pack_conv_tc_planes(wc.to(DEV), fmt)),
+                      (pack.cat_vectors(bt, bt * 2), pack.cat_vectors(bt.to(DEV), bt.to(DEV) * 2)),
+                      (pack.cat_rows(w2[:7], w2[7:20]), pack.cat_rows(w2[:7].to(DEV), w2[7:20].to(DEV)))):
+        assert host.shape == dev.shape and host.dtype == dev.dtype
+        assert torch.equal(host.view(torch.int16) if host.dtype != torch.float32 else host,
+                           dev.cpu().view(torch.int16) if dev.dtype != torch.float32 else dev.cpu())
+    (wh, bh), (wd, bd) = pack.pack_conv_transpose(wt, bt, 8), pack.pack_conv_transpose(wt.to(DEV), bt.to(DEV), 8)
+    assert torch.equal(wh, wd.cpu()) and torch.equal(bh, bd.cpu())
+    assert torch.equal(pack.pack_conv_transpose_tc_planes(wh, fmt).view(torch.int16),
+                       pack.pack_conv_transpose_tc_planes(wd, fmt).cpu().view(torch.int16))
+
+
+def test_f16x2_range_guard():
+    """An activation beyond the fp16 range cannot be split: the result is poisoned (non-finite) and the flag registered
+    with mtts_tc_overflow_bind is raised; in range, the flag stays clear."""
+    from megatts2_b200 import ops
+    dev = torch.device(DEV)
+    ops.tc_overflow(dev)                                            # clear
+    x = torch.randn(256, 128, generator=gen(2)).to(DEV)
+    w = pack.pack_tc_planes((torch.randn(128, 128, generator=gen(3)) / 11).to(DEV), pack.FMT_F16X2)
+    y = ops.linear_tc(x * 6e4 / x.abs().max(), w)
+    assert torch.isfinite(y).all() and not ops.tc_overflow(dev)
+    x[5, 7] = 7.0e4
+    y = ops.linear_tc(x, w)
+    assert not torch.isfinite(y[5]).all()
+    assert torch.isfinite(y[6]).all()
+    assert ops.tc_overflow(dev) and not ops.tc_overflow(dev)        # raised once, reset by the read
+    # the bf16x3 format has the fp32 range
+    y3 = ops.linear_tc(x, pack.pack_tc_planes((torch.randn(128, 128, generator=gen(3)) / 11).to(DEV), pack.FMT_BF16X3))
+    assert torch.isfinite(y3).all() and not ops.tc_overflow(dev)
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_plm_tc_engine_matches_golden_ids(golden, weights_cpu, engine):
     g = golden("plm")
     plm = helpers.build_plm(weights_cpu("plm"), DEV)
-    plm.plm.engine = 1
+    plm.plm.engine = engine
     big = torch.cat([g["tc8"]] * 8, 0).to(DEV)                    # B = 16 so that M = B*(t+1) crosses 128
     ids, logits = plm.infer(big, return_logits=True)
     assert torch.equal(ids.cpu(), torch.cat([g["ids"]] * 8, 0)), "PLM ids must stay bit-exact on the tensor-core engine"
@@ -80,7 +132,8 @@ def test_plm_tc_engine_matches_golden_ids(golden, weights_cpu):
     assert torch.equal(ids0, ids)
 
 
-def test_encoder_tc_vs_ffma(weights_cpu):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_encoder_tc_vs_ffma(weights_cpu, engine):
     from megatts2_b200.modules.transformer import run_encoder
     plm = helpers.build_plm(weights_cpu("plm"), DEV)
     # (8, 40): every dense layer is under-filled -> split-K at full tile width; (16, 64): only the N = 1024 layers;
@@ -89,7 +142,7 @@ def test_encoder_tc_vs_ffma(weights_cpu):
         x = torch.randn(B, T, 1024, generator=gen(3 + i)).to(DEV)
         plm.plm.engine = 0
         y0 = plm.plm(x)
-        plm.plm.engine = 1
+        plm.plm.engine = engine
         y1 = plm.plm(x)
         assert (y0 - y1).abs().max().item() < 5e-4, (B, T)
         assert torch.equal(y1, plm.plm(x)), "the split-K reduction order is fixed: bit-reproducible"
@@ -123,8 +176,9 @@ CONV_TC_CASES = [
 ]
 
 
+@pytest.mark.parametrize("engine", ENGINES)
 @pytest.mark.parametrize("case", CONV_TC_CASES, ids=lambda c: "-".join(f"{k}{v}" for k, v in c.items()))
-def test_conv_tc_vs_fp64(case):
+def test_conv_tc_vs_fp64(case, engine):
     import torch.nn.functional as F
     from megatts2_b200 import ops
     c = dict(dil=1, pad_mode=0, pre=0, post=0, res=False, acc=False, scale=1.0)
@@ -155,7 +209,7 @@ def test_conv_tc_vs_fp64(case):
     kw = dict(k=k, dil=dil, pad=pad, pad_mode=c["pad_mode"], pre_act=c["pre"], pre_slope=0.1, post_act=c["post"],
               res=res.to(DEV) if res is not None else None, out_scale=c["scale"], accumulate=c["acc"])
     y_tc = ops.conv1d(x.to(DEV), pack.pack_conv(w).to(DEV), b.to(DEV), out=y0.clone().to(DEV) if y0 is not None else None,
-                      w_tc=pack.pack_conv_tc_planes(w).to(DEV), **kw)
+                      w_tc=pack.pack_conv_tc_planes(w.to(DEV), fmt_of(engine)), **kw)
     y_ff = ops.conv1d(x.to(DEV), pack.pack_conv(w).to(DEV), b.to(DEV), out=y0.clone().to(DEV) if y0 is not None else None, **kw)
     torch.cuda.synchronize()
     e_tc = (y_tc.cpu().double() - ref).abs().max().item()
@@ -165,7 +219,23 @@ def test_conv_tc_vs_fp64(case):
     assert e_tc < 10 * max(e_ff, 1e-7)
 
 
-def test_conv_stacks_tc_vs_oracle(weights_cpu):
+def test_conv_tc_leaky_post_activation_matches_ffma():
+    """post_act = LEAKY carries its slope on BOTH engines (the tensor-core epilogue used slope 0)."""
+    from megatts2_b200 import _lib as L
+    from megatts2_b200 import ops
+    g = gen(91)
+    x = torch.randn(2, 400, 64, generator=g).to(DEV)
+    w = torch.randn(64, 64, 3, generator=g) / 14
+    kw = dict(k=3, pad=1, post_act=L.ACT_LEAKY, post_slope=0.2)
+    y0 = ops.conv1d(x, pack.pack_conv(w.to(DEV)), **kw)
+    assert (y0 < 0).any()
+    for engine in (1, 2):
+        y1 = ops.conv1d(x, pack.pack_conv(w.to(DEV)), w_tc=pack.pack_conv_tc_planes(w.to(DEV), fmt_of(engine)), **kw)
+        assert (y1 - y0).abs().max().item() < 1e-5
+
+
+@pytest.mark.parametrize("engine", ENGINES)
+def test_conv_stacks_tc_vs_oracle(weights_cpu, engine):
     """Tensor-core conv engine inside the drivers (shapes large enough to be eligible) vs the CPU oracle."""
     from oracle import ref_megatts2 as R
     from oracle import weights as W
@@ -173,7 +243,9 @@ def test_conv_stacks_tc_vs_oracle(weights_cpu):
     mel = torch.randn(4, 203, 80, generator=gen(61)) * 2 - 4
     sd = R.SD(weights_cpu("g"), "vqpe.")
     _, _, _, codes_ref, ze_ref = R.vqpe_forward(sd, mel, W.G_CFG)
-    for eng in (1, 0):
+    for m in (G.mrte.mel_encoder, G.mrte.phone_encoder, G.decoder):
+        m.engine = engine
+    for eng in (engine, 0):
         G.vqpe.convnet.engine = eng
         zq, _, _, codes = G.vqpe(mel.to(DEV))
         assert torch.equal(codes.cpu(), codes_ref), f"VQ codes differ on engine {eng}"
@@ -187,25 +259,27 @@ def test_conv_stacks_tc_vs_oracle(weights_cpu):
     assert (G.decoder(x.to(DEV)).cpu() - dec_ref).abs().max().item() < 5e-4
 
 
-def test_hifigan_full_grid_vs_oracle(weights_cpu):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_hifigan_full_grid_vs_oracle(weights_cpu, engine):
     """B*L large enough that every stage launches full-machine grids inside the fused ResBlock flow."""
     from oracle import ref_megatts2 as R
     from oracle import weights as W
     hifi = helpers.build_hifigan(weights_cpu("hifigan"), DEV)
     mel = torch.randn(4, 80, 64, generator=gen(66)) * 2 - 4
     ref = R.hifigan_generator(weights_cpu("hifigan"), mel, W.HIFIGAN_CFG)
-    hifi.generator.engine = 1
+    hifi.generator.engine = engine
     w1 = hifi.decode_batch(mel.to(DEV))
     assert (w1.cpu() - ref).abs().max().item() < 1e-4
 
 
-def test_hifigan_tc_vs_oracle(weights_cpu):
+@pytest.mark.parametrize("engine", ENGINES)
+def test_hifigan_tc_vs_oracle(weights_cpu, engine):
     from oracle import ref_megatts2 as R
     from oracle import weights as W
     hifi = helpers.build_hifigan(weights_cpu("hifigan"), DEV)
     mel = torch.randn(2, 80, 30, generator=gen(65)) * 2 - 4
     ref = R.hifigan_generator(weights_cpu("hifigan"), mel, W.HIFIGAN_CFG)
-    hifi.generator.engine = 1
+    hifi.generator.engine = engine
     w1 = hifi.decode_batch(mel.to(DEV))
     hifi.generator.engine = 0
     w0 = hifi.decode_batch(mel.to(DEV))

@@ -38,7 +38,7 @@ def main():
     t0 = time.perf_counter()
     tts = bench.build_product(dev)
     say(f"build_product: {time.perf_counter() - t0:.1f} s")
-    wav, phone, forced = bench.make_inputs(a.batch, 1234)
+    wav, phone, forced = bench.make_inputs(range(a.batch))
     wav, phone, forced = wav.to(dev), phone.to(dev), forced.to(dev)
     for rep in range(a.reps):
         say(f"== pass {rep} (batch {a.batch})")
@@ -51,6 +51,7 @@ def main():
         codes, _ = timed("plm.infer", lambda: tts.plm.infer(tc8))
         melo, _ = timed("decode_mel", lambda: tts.generator.decode_mel_cl(exp, codes))
         wv, _ = timed("hifigan", lambda: tts.hifi_gan.decode_batch_cl(melo))
+        _, _ = timed("hifigan (prompt re-vocode)", lambda: tts.hifi_gan.decode_batch_cl(mel))
         say(f"  launches this pass: {ops.launch_count() - n0}; wav {tuple(wv.shape)} finite={bool(torch.isfinite(wv).all())}")
     _, dt = timed("full gpu_step", lambda: bench.gpu_step(tts, wav, phone, forced))
     say(f"samples/s = {a.batch * bench.SAMPLES_PER_UTT / dt:.0f}")
