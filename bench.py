@@ -63,6 +63,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU leg (profiling runs)")
     ap.add_argument("--no-prompt-revocode", action="store_true", help="leave out the prompt re-vocoding of forward()")
     ap.add_argument("--cpu-workers", type=int, default=0, help="concurrent batch-1 CPU workers (0 = cpus / 8, at most 16)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads per CPU worker (0 = 8)")
     ap.add_argument("--clips", type=int, default=10000, help="--config c2: number of 3-s clips")
     return ap.parse_args()
 
@@ -214,11 +215,12 @@ def _worker_utt(job):
 
 
 class CpuPool:
-    def __init__(self, workers):
+    def __init__(self, workers, threads=0):
         import multiprocessing as mp
         ncpu = os.cpu_count() or 1
-        self.workers = workers if workers > 0 else max(1, min(16, ncpu // THREADS_PER_WORKER))
-        self.threads = max(1, min(THREADS_PER_WORKER, ncpu // self.workers))
+        tpw = threads if threads > 0 else THREADS_PER_WORKER
+        self.workers = workers if workers > 0 else max(1, min(16, ncpu // tpw))
+        self.threads = max(1, min(tpw, ncpu // self.workers))
         self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_worker_init, initargs=(self.threads,))
         self.pool.map(_noop, range(self.workers))      # every worker has imported torch and rebuilt the weights
 
@@ -420,7 +422,7 @@ def cpu_check(args, gpu, lo, revocode):
     box's host cores over `check_utts` utterances of this rank's batch: it is the CHECKER of the GPU arm's prosody ids /
     durations / mel (the parity half of the metric), and its wall time is the `cpu_baseline`."""
     n = min(args.check_utts, args.batch)
-    pool = CpuPool(args.cpu_workers)
+    pool = CpuPool(args.cpu_workers, args.cpu_threads)
     log(f"cpu check: {n} utterances on {pool.workers} workers x {pool.threads} threads ({os.cpu_count()} host cpus)")
     t0 = time.perf_counter()
     res = pool.run([lo + i for i in range(n)], revocode)
@@ -460,7 +462,7 @@ def run_reference(args):
     if rank != 0:
         return None
     revocode = not args.no_prompt_revocode
-    pool = CpuPool(args.cpu_workers)
+    pool = CpuPool(args.cpu_workers, args.cpu_threads)
     W = pool.workers
     log(f"reference arm: {W} workers x {pool.threads} torch threads of {os.cpu_count()} host cpus")
     nxt = 0

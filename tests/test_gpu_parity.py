@@ -245,8 +245,8 @@ def test_vq_search_golden(golden, weights_cpu):
     helpers.record("vq_adversarial_fixture", dict(rows=int(idx.numel()), mismatches=int(mism.sum()), bit_exact_rate=rate,
                                                   max_gap64_of_a_mismatch=float(g["gap64"][mism].max()) if mism.any() else 0.0))
     # the fixture's second block is BUILT from near-ties (fp64 gap of the two best codes below fp32 rounding of
-    # |x|^2 + |e|^2 ~ 500); the achieved rate is recorded by helpers.record -> profiles/r2_parity_rates.json
-    assert rate > 0.97
+    # |x|^2 + |e|^2 ~ 500); measured on B200: 0 mismatches of 1088 rows (profiles/r2_parity_rates.jsonl), so the bar is 1.0
+    assert rate == 1.0
     assert torch.equal(idx[:512], ref[:512])                 # the random (non-adversarial) block
     assert torch.equal(idx[-64:], torch.arange(64))          # exact codes map to themselves
     dec = ops.vq_gather(ref.view(1, -1).to(DEV), embed)
@@ -486,7 +486,7 @@ def test_prompt_revocode_and_synthesize_many(weights_cpu):
     # speechbrain's decode_batch(mel, mel_lens, hop_len) zeroes the samples past mel_lens * hop_len
     w = tts.hifi_gan.decode_batch(melp.transpose(1, 2), mel_lens=torch.tensor([48, 30]), hop_len=256)
     assert float(w[1, :, 30 * 256:].abs().max()) == 0.0 and float(w[1, :, :30 * 256].abs().max()) > 0
-    assert torch.equal(w[0], pw[0])
+    assert torch.equal(w[0, :, :48 * 256], pw[0, :, :48 * 256]) and float(w[0, :, 48 * 256:].abs().max()) == 0.0
 
 
 def test_batch_invariance_property(weights_cpu, PLM):

@@ -22,7 +22,7 @@ def main():
     a = ap.parse_args()
     dev = torch.device("cuda", 0)
     tts = bench.build_product(dev)
-    wav, phone, forced = bench.make_inputs(a.batch, 1234)
+    wav, phone, forced = bench.make_inputs(range(a.batch))
     wav, phone, forced = wav.to(dev), phone.to(dev), forced.to(dev)
     from megatts2_b200 import ops
     from megatts2_b200.modules.tokenizer import extract_mel_spec
