@@ -48,7 +48,10 @@ SAMPLES_PER_UTT = TP * DUR * 256                      # 131,072 mel-aligned samp
 METRIC = "synthesized_audio_samples_per_sec_batch64"
 UNIT = "samples/s"
 SEED0 = 1234
-THREADS_PER_WORKER = 8                                # the CPU arm: concurrent batch-1 workers of this many torch threads
+THREADS_PER_WORKER = 16                               # the CPU arm: concurrent batch-1 workers of this many torch threads
+MAX_WORKERS = 4                                       # (measured on the 128-cpu GPU box, profiles/r2b_cpu_arm_sweep.log: the batch-1
+#                                                       AR loops stream 0.7 GB of weights per step and are memory-bound - 4 x 16
+#                                                       threads is the fastest split; 16 x 8 is 4 % slower, 1 x 64 is 2x slower)
 
 
 def parse():
@@ -62,8 +65,8 @@ def parse():
     ap.add_argument("--check-utts", type=int, default=16, help="utterances of the batch checked against the CPU oracle")
     ap.add_argument("--no-cpu-baseline", action="store_true", help="skip the bounded CPU leg (profiling runs)")
     ap.add_argument("--no-prompt-revocode", action="store_true", help="leave out the prompt re-vocoding of forward()")
-    ap.add_argument("--cpu-workers", type=int, default=0, help="concurrent batch-1 CPU workers (0 = cpus / 8, at most 16)")
-    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads per CPU worker (0 = 8)")
+    ap.add_argument("--cpu-workers", type=int, default=0, help="concurrent batch-1 CPU workers (0 = cpus / 16, at most 4)")
+    ap.add_argument("--cpu-threads", type=int, default=0, help="torch threads per CPU worker (0 = 16)")
     ap.add_argument("--clips", type=int, default=10000, help="--config c2: number of 3-s clips")
     return ap.parse_args()
 
@@ -219,7 +222,7 @@ class CpuPool:
         import multiprocessing as mp
         ncpu = os.cpu_count() or 1
         tpw = threads if threads > 0 else THREADS_PER_WORKER
-        self.workers = workers if workers > 0 else max(1, min(16, ncpu // tpw))
+        self.workers = workers if workers > 0 else max(1, min(MAX_WORKERS, ncpu // tpw))
         self.threads = max(1, min(tpw, ncpu // self.workers))
         self.pool = mp.get_context("spawn").Pool(self.workers, initializer=_worker_init, initargs=(self.threads,))
         self.pool.map(_noop, range(self.workers))      # every worker has imported torch and rebuilt the weights

@@ -93,6 +93,8 @@ int mask_tail(float* x, int B, int rows, int L, const int32_t* keep, cudaStream_
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,
               int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, cudaStream_t st);
 int attention(const mtts_attn_params& p, cudaStream_t st);
+bool attention_tc_eligible(const mtts_attn_params& p);
+int attention_tc(const mtts_attn_params& p, cudaStream_t st);   // tcgen05 (attn_tc.cu)
 int vq_argmin(const float* x, int ldx, const float* embed, int64_t N, int D, int K, int64_t* idx, cudaStream_t st);
 int vq_gather(const int64_t* idx, int idx_ld, const float* embed, int D, int K, int B, int T_out, int repeat, float* y,
               int64_t y_sb, int ldy, cudaStream_t st);

@@ -3,6 +3,7 @@
 // and the per-step helpers of the PLM / ADM autoregressive loops.
 #include <float.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -385,6 +386,17 @@ int attention(const mtts_attn_params& p, cudaStream_t st) {
   MTTS_REQUIRE(p.B >= 0 && p.H > 0 && p.Tq >= 0 && p.Tk > 0, "bad dims");
   MTTS_REQUIRE(p.H <= 65535 && p.B <= 65535, "grid too large");
   if (p.B == 0 || p.Tq == 0) return 0;
+  // tensor-core path (attn_tc.cu): the head dims of the AR stacks once the sequence feeds a 128-row MMA reasonably
+  // (MEGATTS2_ATTN_TC = 0 disables it, MEGATTS2_ATTN_TC_MIN sets the minimum Tq; read once per process)
+  {
+    static const int tc_min = [] {
+      const char* e = getenv("MEGATTS2_ATTN_TC");
+      if (e && e[0] == '0') return 1 << 30;
+      const char* m = getenv("MEGATTS2_ATTN_TC_MIN");
+      return m ? atoi(m) : 16;
+    }();
+    if (p.Tq >= tc_min && attention_tc_eligible(p)) return attention_tc(p, st);
+  }
   // dh <= 128: one CTA of 8 warps covers a whole AR-step sequence (Tq <= 64), so K and V are read once per (b, h);
   // the rows are dealt evenly to the warps (RW = ceil(Tq / 8) rows each) - with a fixed 8 rows per warp a 35-row
   // step left three of the eight warps idle.  Row results do not depend on RW (each row's sums keep their order).

@@ -194,7 +194,9 @@ def test_layernorm(C_):
 
 
 @pytest.mark.parametrize("H,dh,Tq,Tk", [(16, 64, 70, 70), (8, 96, 33, 33), (2, 256, 12, 12), (1, 512, 64, 31),
-                                        (16, 64, 1, 200), (4, 128, 17, 65)])
+                                        (16, 64, 1, 200), (4, 128, 17, 65),
+                                        # tensor-core path (attn_tc.cu): one / several query tiles and key tiles, ragged edges
+                                        (16, 64, 64, 64), (16, 64, 130, 300), (8, 96, 200, 200), (8, 96, 16, 16), (2, 128, 129, 64)])
 def test_attention(H, dh, Tq, Tk):
     from megatts2_b200 import ops
     g = gen(H * 1000 + dh + Tq)
