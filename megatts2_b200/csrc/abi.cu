@@ -2,6 +2,7 @@
 // drivers.cu.)  No C++ exception crosses this boundary; errors are negative codes plus a
 // thread-local message.
 #include <algorithm>
+#include <stdlib.h>
 
 #include "kernels.h"
 
@@ -13,6 +14,14 @@
 namespace mtts {
 thread_local char g_err[512] = "";
 std::atomic<int64_t> g_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = getenv("MEGATTS2_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 bool g_trace_on = false;
 static std::mutex g_trace_mu;

@@ -68,6 +68,7 @@ template <int DH>
 __global__ void __launch_bounds__(128)
 attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
   using Cfg = AtcCfg<DH>;
+  pdl_trigger();
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* sm = smem_raw + (base - smem_u32(smem_raw));
@@ -75,7 +76,8 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
   const uint32_t tmem_slot = bar + 16;
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(sm + Cfg::OFF_P + 2 * Cfg::P_PLANE + 16);
 
-  const int tid = threadIdx.x, warp = tid >> 5;
+  const int tid = threadIdx.x;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);        // warp-uniform for the compiler (uniform-register MMA operands)
   const int q0 = blockIdx.x * 128, h = blockIdx.y, b = blockIdx.z;
   const int qrow = q0 + tid;
   const bool qvalid = qrow < p.Tq;
@@ -89,6 +91,7 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
 
+  pdl_wait();
   bool bad = false;
   // ---- stage Q: thread r splits its own row (rows past Tq are zero)
   {
@@ -111,7 +114,8 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  const uint32_t tmem = *tmem_slot_ptr;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+  const uint32_t leader = (warp == 0 && elect_one()) ? 1u : 0u;
   const uint32_t lane_addr = tmem + ((uint32_t)(warp * 32) << 16);      // this warp's TMEM lane quarter
 
   float m_run = -INFINITY, l_run = 0.f;
@@ -175,8 +179,8 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
     fence_proxy_async_smem();
     tc_fence_before();       // every thread's TMEM reads of the previous tile (O) are complete before the MMAs overwrite it
     __syncthreads();
-    // ---- S = Q K^T
-    if (tid == 0) {
+    // ---- S = Q K^T   (warp 0 walks the issue loop uniformly; its elected lane executes the MMAs)
+    if (warp == 0) {
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < DH / 16; ++ks) {
@@ -184,11 +188,11 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
         const uint32_t ka = base + Cfg::OFF_K + (ks >> 1) * Cfg::K_SLAB + (ks & 1) * 32;
         const uint64_t a1 = desc_hi | (uint64_t)((qa >> 4) & 0x3FFF), a2 = desc_hi | (uint64_t)(((qa + Cfg::Q_PLANE) >> 4) & 0x3FFF);
         const uint64_t b1 = desc_hi | (uint64_t)((ka >> 4) & 0x3FFF), b2 = desc_hi | (uint64_t)(((ka + Cfg::K_PLANE) >> 4) & 0x3FFF);
-        tc_mma_bf16(tmem + ATC_NK, a1, b2, IDESC_S, ks ? 1u : 0u);      // correction: q1 k2' + q2' k1
-        tc_mma_bf16(tmem + ATC_NK, a2, b1, IDESC_S, 1u);
-        tc_mma_bf16(tmem, a1, b1, IDESC_S, ks ? 1u : 0u);               // main: q1 k1
+        tc_mma_l(tmem + ATC_NK, a1, b2, IDESC_S, ks ? 1u : 0u, leader);      // correction: q1 k2' + q2' k1
+        tc_mma_l(tmem + ATC_NK, a2, b1, IDESC_S, 1u, leader);
+        tc_mma_l(tmem, a1, b1, IDESC_S, ks ? 1u : 0u, leader);               // main: q1 k1
       }
-      tc_commit(bar);
+      tc_commit_l(bar, leader);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -236,7 +240,7 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
     tc_fence_before();       // this thread's reads of S are complete before O overwrites the columns
     __syncthreads();
     // ---- O_tile = P V   (K = the tile's 64 keys: 4 k-steps)
-    if (tid == 0) {
+    if (warp == 0) {
       tc_fence_after();
 #pragma unroll
       for (int ks = 0; ks < ATC_NK / 16; ++ks) {
@@ -244,11 +248,11 @@ attn_tc_kernel(const mtts_attn_params p, int32_t* ovf) {
         const uint32_t va = base + Cfg::OFF_V + (ks >> 1) * Cfg::V_SLAB + (ks & 1) * 32;
         const uint64_t a1 = desc_hi | (uint64_t)((pa >> 4) & 0x3FFF), a2 = desc_hi | (uint64_t)(((pa + Cfg::P_PLANE) >> 4) & 0x3FFF);
         const uint64_t b1 = desc_hi | (uint64_t)((va >> 4) & 0x3FFF), b2 = desc_hi | (uint64_t)(((va + Cfg::V_PLANE) >> 4) & 0x3FFF);
-        tc_mma_bf16(tmem + DH, a1, b2, IDESC_O, ks ? 1u : 0u);
-        tc_mma_bf16(tmem + DH, a2, b1, IDESC_O, 1u);
-        tc_mma_bf16(tmem, a1, b1, IDESC_O, ks ? 1u : 0u);
+        tc_mma_l(tmem + DH, a1, b2, IDESC_O, ks ? 1u : 0u, leader);
+        tc_mma_l(tmem + DH, a2, b1, IDESC_O, 1u, leader);
+        tc_mma_l(tmem, a1, b1, IDESC_O, ks ? 1u : 0u, leader);
       }
-      tc_commit(bar);
+      tc_commit_l(bar, leader);
     }
     mbar_wait(bar, phase);
     phase ^= 1;
@@ -304,7 +308,7 @@ int attn_tc_launch(const mtts_attn_params& p, cudaStream_t st) {
     configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   dim3 grid((unsigned)cdiv64(p.Tq, 128), (unsigned)p.H, (unsigned)p.B);
-  attn_tc_kernel<DH><<<grid, 128, Cfg::SMEM, st>>>(p, tc_ovf_ptr());
+  launch_k(attn_tc_kernel<DH>, grid, 128, Cfg::SMEM, st, p, tc_ovf_ptr());
   MTTS_CHECK_LAUNCH();
   return 0;
 }

@@ -43,6 +43,30 @@ extern bool g_trace_on;
     if (r__ != 0) return r__;                                                        \
   } while (0)
 
+// ---- programmatic dependent launch (PDL).  Every kernel of the library starts with pdl_entry() (or, for the kernels with
+// a real prologue - barrier init, TMEM allocation, descriptor prefetch - pdl_trigger() at entry and pdl_wait() before the
+// first access to global memory): launch_dependents lets the NEXT kernel of the stream be scheduled while this one still
+// runs, and the wait blocks it until this grid has completed and flushed, so only launch latency and prologues overlap -
+// never data.  Launches go through launch_k(), which sets the stream-serialisation attribute (MEGATTS2_PDL=0 disables it;
+// the device-side instructions are no-ops for a kernel launched without the attribute).
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() {
+  pdl_trigger();
+  pdl_wait();
+}
+bool pdl_enabled();
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);      // a failure is picked up by MTTS_CHECK_LAUNCH
+}
+
 static inline int64_t cdiv64(int64_t a, int64_t b) { return (a + b - 1) / b; }
 static inline int64_t align_up(int64_t a, int64_t b) { return cdiv64(a, b) * b; }
 

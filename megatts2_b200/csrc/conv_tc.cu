@@ -44,29 +44,38 @@ struct ConvTcArgs {
   // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
   int32_t splits; float* partial;
   int32_t fmt; int32_t* ovf;   // operand format of the plane output (== the kernel's own NP) and the f16 range flag
+  int32_t bo_mode;             // halo form, diagnostics: 1 = put (addr >> 7) & 7 into the descriptors' base-offset field (WRONG on B200)
 };
 
 // PAIR = 1: two CTAs of a cluster run one 256 x BN tile with cta_group::2 MMAs; each CTA stages its own 128 rows of
 // the activations and HALF of the weight tile, so the L2 -> SM traffic per FLOP drops by a quarter
-template <int BN, int SWB, int PAIR = 0, int NP = 3>
+// HALO = 1 (convolutions whose input channels fit ONE K-slab, Cin <= SWB / 2): the activation tile of an output tile -
+// its 128 rows plus the dil * (k - 1) halo rows - is loaded ONCE into a double-buffered region and every tap reads it
+// through a row-shifted UMMA descriptor; only the (tiny) per-tap weight tiles stream through the stage ring.  The plain
+// form re-reads the tile once per tap (k-fold L2 -> SM traffic), which is what bounds the C = 32 / 64 HiFi-GAN stages.
+constexpr int CTC_HALO_ROWS = 192;     // rows of a halo tile buffer: 128 + dil * (k - 1) <= 192, a multiple of 8
+template <int BN, int SWB, int PAIR = 0, int NP = 3, int HALO = 0>
 struct ConvTcCfg {
+  static_assert(!(PAIR && HALO), "the halo form is single-CTA");
   static constexpr int BK = SWB / 2;                       // bf16 elements per swizzled row
-  static constexpr int A_PLANE = 128 * SWB;
+  static constexpr int A_PLANE = (HALO ? CTC_HALO_ROWS : 128) * SWB;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by one CTA
   static constexpr int B_PLANE = B_ROWS * SWB;
-  static constexpr int STAGE = NP * (A_PLANE + B_PLANE);
+  static constexpr int STAGE = HALO ? NP * B_PLANE : NP * (A_PLANE + B_PLANE);
+  static constexpr int A_REGION = HALO ? 2 * NP * A_PLANE : 0;   // two halo-tile buffers
   static constexpr int EPI_STAGE = 8 * 32 * 20 * 4;          // epilogue transpose buffers: 8 warps x [32 rows][20 floats]
-  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE) / STAGE;
+  static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE - A_REGION) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
-  static constexpr int SMEM = STAGES * STAGE + 1024 + 256 + EPI_STAGE;
+  static constexpr int SMEM = A_REGION + STAGES * STAGE + 1024 + 256 + EPI_STAGE;
   static constexpr int NACC = (4 * BN > 512) ? 1 : 2;            // accumulator buffers: BN = 256 fills TMEM with one
   static constexpr int TMEM_COLS = NACC * 2 * BN < 32 ? 32 : NACC * 2 * BN;   // NACC x (main + correction) x BN
 };
 
-template <int BN, int SWB, int PAIR, int NP>
+template <int BN, int SWB, int PAIR, int NP, int HALO>
 __global__ void __launch_bounds__(384, 1)
 conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
-  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP>;
+  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP, HALO>;
+  pdl_trigger();                                           // the next kernel may be scheduled; it waits for this grid itself
   constexpr int BM = PAIR ? 256 : 128;                     // rows of one (pair) tile
   const uint32_t crank = PAIR ? cluster_ctarank() : 0u;
   const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // tile walker id (a CTA or a CTA pair)
@@ -74,15 +83,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
   constexpr int STAGES = Cfg::STAGES;
   constexpr int NACC = Cfg::NACC;
   extern __shared__ uint8_t smem_raw[];
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t smem_a = (smem_u32(smem_raw) + 1023u) & ~1023u;      // HALO: the two halo-tile buffers come first
+  const uint32_t smem_base = smem_a + Cfg::A_REGION;                   // the stage ring
   const uint32_t bars = smem_base + STAGES * Cfg::STAGE;
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
+  const uint32_t afull_bar = tmem_slot + 16, aempty_bar = afull_bar + 16;   // HALO only (8 * STAGES * 2 + 80 <= 256)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* epi_stage = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // 16-byte aligned
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);   // warp-uniform as far as the compiler can tell
+  const int lane = threadIdx.x & 31;
   const int num_t = (g.T + BM - 1) / BM, num_n = (g.Cout + BN - 1) / BN;
   const int num_tiles = g.B * num_t * num_n * g.splits;      // work items: (tile, K split)
   const int ncb = (g.Cin + Cfg::BK - 1) / Cfg::BK;
@@ -103,6 +115,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, PAIR ? 16 : 8);     // one arrive per epilogue warp (8 warps per CTA)
+      if constexpr (HALO) {
+        mbar_init(afull_bar + 8 * s, 1);
+        mbar_init(aempty_bar + 8 * s, 1);
+      }
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -121,19 +137,49 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
   __syncthreads();
   if constexpr (PAIR) cluster_sync_all();      // the peer's barriers are initialised before anything signals them
   tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot_ptr;
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot_ptr, 0);
+  pdl_wait();        // everything above (barriers, TMEM, descriptor prefetch) overlapped the previous kernel's tail
 
+  // The two issuing roles run WARP-UNIFORMLY: every lane walks the loops and computes the (identical) addresses and
+  // descriptors, and one elected lane executes the TMA / MMA / commit instructions.  Those instructions take their
+  // operands from uniform registers; issued from inside a single-lane branch (the round-1 form) ptxas wraps EACH of
+  // them in ELECT + 5 x R2UR + a waterfall loop, about 100 cycles per tcgen05.mma - measured as the limiter of every
+  // tile shape (ncu source page: the issuing warp never waits, profiles/r2e_mma_issue_bound.md).
   if (warp == 0) {
-    // ================= TMA producer: the whole warp walks the pipeline; lanes 0..2*NP-1 each issue ONE of the
-    // bulk copies of a K-slab (A planes, B planes) so the copies are issued concurrently - with one issuing
-    // thread the ~6 x 100-150 cycles of issue latency per slab bound the small-channel convs
+    // ================= TMA producer =================
+    const bool leader = elect_one();
     int stage = 0, phase = 0;
+    [[maybe_unused]] int ait = 0;
     for (int item = worker; item < num_tiles; item += nworkers) {
       const int sp = item % g.splits, tile = item / g.splits;
       const int kb0 = (int)((int64_t)sp * num_k / g.splits), kb1 = (int)((int64_t)(sp + 1) * num_k / g.splits);
       const int nb = tile % num_n, r = tile / num_n;
       const int tb = r % num_t, b = r / num_t;
       const int trow = tb * BM + (int)crank * 128;               // this CTA's first output row
+      if constexpr (HALO) {
+        // the tile's activation rows [trow, trow + 128 + dil * (k - 1)) once, then one weight tile per tap
+        const int ab = ait & 1, aph = (ait >> 1) & 1;
+        ++ait;
+        mbar_wait(aempty_bar + 8 * ab, aph ^ 1);
+        if (leader) {
+          mbar_expect_tx(afull_bar + 8 * ab, (uint32_t)(NP * (128 + g.dil * (g.k - 1)) * SWB));
+#pragma unroll
+          for (int q = 0; q < NP; ++q)
+            tma_load_3d(smem_a + (ab * NP + q) * Cfg::A_PLANE, &maps.a[q], afull_bar + 8 * ab, 0, trow, b);
+        }
+        for (int kb = kb0; kb < kb1; ++kb) {
+          mbar_wait(empty_bar + 8 * stage, phase ^ 1);
+          const uint32_t sb = smem_base + stage * Cfg::STAGE;
+          const uint32_t fb = full_bar + 8 * stage;
+          if (leader) {
+            mbar_expect_tx(fb, Cfg::STAGE);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) tma_load_2d(sb + q * Cfg::B_PLANE, &maps.b[q], fb, 0, kb * g.Cout + nb * BN);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        continue;
+      }
       for (int kb = kb0; kb < kb1; ++kb) {
         const int j = kb / ncb, cb = kb - j * ncb;
         mbar_wait(empty_bar + 8 * stage, phase ^ 1);
@@ -142,27 +188,33 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         if constexpr (PAIR) {
           // both CTAs' bytes are counted on the LEADER's barrier (the leader issues the MMAs for the pair)
           const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);
-          if (lane == 0 && crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE);
-          __syncwarp();
-          if (lane < NP) tma_load_3d_2sm(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
-          else if (lane < 2 * NP)
-            tma_load_2d_2sm(sb + (lane - NP) * Cfg::B_PLANE, &maps.b[lane - NP], fb, cb * Cfg::BK,
-                            j * g.Cout + nb * BN + (int)crank * Cfg::B_ROWS);
+          if (leader) {
+            if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) tma_load_3d_2sm(sa + q * Cfg::A_PLANE, &maps.a[q], fb, cb * Cfg::BK, trow + j * g.dil, b);
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+              tma_load_2d_2sm(sb + q * Cfg::B_PLANE, &maps.b[q], fb, cb * Cfg::BK, j * g.Cout + nb * BN + (int)crank * Cfg::B_ROWS);
+          }
         } else {
           const uint32_t fb = full_bar + 8 * stage;
-          if (lane == 0) mbar_expect_tx(fb, Cfg::STAGE);
-          __syncwarp();
-          if (lane < NP) tma_load_3d(sa + lane * Cfg::A_PLANE, &maps.a[lane], fb, cb * Cfg::BK, trow + j * g.dil, b);
-          else if (lane < 2 * NP) tma_load_2d(sb + (lane - NP) * Cfg::B_PLANE, &maps.b[lane - NP], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+          if (leader) {
+            mbar_expect_tx(fb, Cfg::STAGE);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) tma_load_3d(sa + q * Cfg::A_PLANE, &maps.a[q], fb, cb * Cfg::BK, trow + j * g.dil, b);
+#pragma unroll
+            for (int q = 0; q < NP; ++q) tma_load_2d(sb + q * Cfg::B_PLANE, &maps.b[q], fb, cb * Cfg::BK, j * g.Cout + nb * BN);
+          }
         }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else if (warp == 1) {
-    if (lane == 0 && crank == 0) {   // ================= MMA issuer (the leader CTA issues for a pair) =================
+    if (crank == 0) {   // ================= MMA issuer (the leader CTA issues for a pair) =================
+      const uint32_t leader = elect_one() ? 1u : 0u;
       // instruction descriptor: D = f32, A / B = bf16 (1) or f16 (0), K-major, N >> 3, M >> 4
-      const uint32_t ab = NP == 3 ? ((1u << 7) | (1u << 10)) : 0u;
-      const uint32_t idesc = (1u << 4) | ab | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      const uint32_t ab_fmt = NP == 3 ? ((1u << 7) | (1u << 10)) : 0u;
+      const uint32_t idesc = (1u << 4) | ab_fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
       const uint64_t desc_base = umma_desc_kmajor<SWB>(0u);      // everything except the start address
       int stage = 0, phase = 0, it = 0;
       for (int item = worker; item < num_tiles; item += nworkers, ++it) {
@@ -173,6 +225,49 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         tc_fence_after();
         const uint32_t d_main = tmem_base + as * (2 * BN);
         const uint32_t d_corr = d_main + BN;
+        if constexpr (HALO) {
+          const int ab = it & 1, aph = (it >> 1) & 1;
+          mbar_wait(afull_bar + 8 * ab, aph);
+          for (int kb = kb0; kb < kb1; ++kb) {          // kb == tap (one K-slab per tap)
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            // A: the halo tile shifted by kb * dil rows.  The swizzle is a function of the shared-memory ADDRESS bits (the
+            // TMA wrote with them, the MMA reads with them), so a start address that is a whole number of rows into the
+            // tile needs nothing else: measured on B200, every parity case passes with the descriptor's base-offset field
+            // left at zero and fails with (addr >> 7) & 7 in it (gpurun call D, profiles/r2d_halo_form.md).
+            const uint32_t a_addr = smem_a + ab * NP * Cfg::A_PLANE + (uint32_t)(kb * g.dil) * SWB;
+            const uint32_t b_addr = smem_base + stage * Cfg::STAGE;
+            const uint32_t first = (kb == kb0) ? 0u : 1u;
+#pragma unroll
+            for (int ks = 0; ks < Cfg::BK / 16; ++ks) {
+              const uint32_t aa = a_addr + ks * 32, bb = b_addr + ks * 32;
+              const uint64_t a1 = umma_desc_shifted(desc_base, aa, g.bo_mode), a2 = umma_desc_shifted(desc_base, aa + Cfg::A_PLANE, g.bo_mode);
+              const uint64_t b1 = desc_base | (uint64_t)((bb >> 4) & 0x3FFF), b2 = desc_base | (uint64_t)(((bb + Cfg::B_PLANE) >> 4) & 0x3FFF);
+              const uint32_t f = (ks == 0) ? first : 1u;
+              if constexpr (NP == 2) {
+                tc_mma_l(d_corr, a1, b2, idesc, f, leader);
+                tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
+                tc_mma_l(d_main, a1, b1, idesc, f, leader);
+              } else {
+                const uint64_t a3 = umma_desc_shifted(desc_base, aa + 2 * Cfg::A_PLANE, g.bo_mode);
+                const uint64_t b3 = desc_base | (uint64_t)(((bb + 2 * Cfg::B_PLANE) >> 4) & 0x3FFF);
+                tc_mma_l(d_corr, a2, b2, idesc, f, leader);
+                tc_mma_l(d_corr, a1, b3, idesc, 1u, leader);
+                tc_mma_l(d_corr, a3, b1, idesc, 1u, leader);
+                tc_mma_l(d_corr, a1, b2, idesc, 1u, leader);
+                tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
+                tc_mma_l(d_main, a1, b1, idesc, f, leader);
+              }
+            }
+            tc_commit_l(empty_bar + 8 * stage, leader);
+            if (kb == kb1 - 1) {
+              tc_commit_l(aempty_bar + 8 * ab, leader);           // the halo tile is free once this tile's MMAs have retired
+              tc_commit_l(tfull_bar + 8 * as, leader);
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        }
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(full_bar + 8 * stage, phase);
           tc_fence_after();
@@ -188,36 +283,36 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
             if constexpr (NP == 2) {
               (void)a3; (void)b3;
               if constexpr (PAIR) {
-                tc_mma_bf16_2sm(d_corr, a1, b2, idesc, f);    // x1 w2'
-                tc_mma_bf16_2sm(d_corr, a2, b1, idesc, 1u);   // x2' w1
-                tc_mma_bf16_2sm(d_main, a1, b1, idesc, f);    // x1 w1
+                tc_mma_2sm_l(d_corr, a1, b2, idesc, f, leader);    // x1 w2'
+                tc_mma_2sm_l(d_corr, a2, b1, idesc, 1u, leader);   // x2' w1
+                tc_mma_2sm_l(d_main, a1, b1, idesc, f, leader);    // x1 w1
               } else {
-                tc_mma_bf16(d_corr, a1, b2, idesc, f);
-                tc_mma_bf16(d_corr, a2, b1, idesc, 1u);
-                tc_mma_bf16(d_main, a1, b1, idesc, f);
+                tc_mma_l(d_corr, a1, b2, idesc, f, leader);
+                tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
+                tc_mma_l(d_main, a1, b1, idesc, f, leader);
               }
             } else if constexpr (PAIR) {
-              tc_mma_bf16_2sm(d_corr, a2, b2, idesc, f);
-              tc_mma_bf16_2sm(d_corr, a1, b3, idesc, 1u);
-              tc_mma_bf16_2sm(d_corr, a3, b1, idesc, 1u);
-              tc_mma_bf16_2sm(d_corr, a1, b2, idesc, 1u);
-              tc_mma_bf16_2sm(d_corr, a2, b1, idesc, 1u);
-              tc_mma_bf16_2sm(d_main, a1, b1, idesc, f);
+              tc_mma_2sm_l(d_corr, a2, b2, idesc, f, leader);
+              tc_mma_2sm_l(d_corr, a1, b3, idesc, 1u, leader);
+              tc_mma_2sm_l(d_corr, a3, b1, idesc, 1u, leader);
+              tc_mma_2sm_l(d_corr, a1, b2, idesc, 1u, leader);
+              tc_mma_2sm_l(d_corr, a2, b1, idesc, 1u, leader);
+              tc_mma_2sm_l(d_main, a1, b1, idesc, f, leader);
             } else {
-              tc_mma_bf16(d_corr, a2, b2, idesc, f);      // x2 w2   (smallest terms first)
-              tc_mma_bf16(d_corr, a1, b3, idesc, 1u);     // x1 w3
-              tc_mma_bf16(d_corr, a3, b1, idesc, 1u);     // x3 w1
-              tc_mma_bf16(d_corr, a1, b2, idesc, 1u);     // x1 w2
-              tc_mma_bf16(d_corr, a2, b1, idesc, 1u);     // x2 w1
-              tc_mma_bf16(d_main, a1, b1, idesc, f);      // x1 w1
+              tc_mma_l(d_corr, a2, b2, idesc, f, leader);      // x2 w2   (smallest terms first)
+              tc_mma_l(d_corr, a1, b3, idesc, 1u, leader);     // x1 w3
+              tc_mma_l(d_corr, a3, b1, idesc, 1u, leader);     // x3 w1
+              tc_mma_l(d_corr, a1, b2, idesc, 1u, leader);     // x1 w2
+              tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);     // x2 w1
+              tc_mma_l(d_main, a1, b1, idesc, f, leader);      // x1 w1
             }
           }
           if constexpr (PAIR) {
-            tc_commit_2sm(empty_bar + 8 * stage);          // frees the stage in both CTAs
-            if (kb == kb1 - 1) tc_commit_2sm(tfull_bar + 8 * as);
+            tc_commit_2sm_l(empty_bar + 8 * stage, leader);          // frees the stage in both CTAs
+            if (kb == kb1 - 1) tc_commit_2sm_l(tfull_bar + 8 * as, leader);
           } else {
-            tc_commit(empty_bar + 8 * stage);
-            if (kb == kb1 - 1) tc_commit(tfull_bar + 8 * as);
+            tc_commit_l(empty_bar + 8 * stage, leader);
+            if (kb == kb1 - 1) tc_commit_l(tfull_bar + 8 * as, leader);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -340,6 +435,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
 // (bias -> activation -> residual -> scale -> accumulate -> fp32 and/or bf16x3 plane store)
 __global__ void __launch_bounds__(256)
 tc_splitk_reduce_kernel(const ConvTcArgs g, int64_t total4) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = g.Cout / 4;
@@ -383,6 +479,7 @@ __global__ void __launch_bounds__(256)
 split_pad_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int C, int hl, int Tp, int pad_mode,
                  int pre_act, float slope, __nv_bfloat16* __restrict__ planes, int64_t plane_stride,
                  int64_t total4, int fmt, int32_t* ovf) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int cq = C >> 2;
@@ -414,6 +511,7 @@ split_pad_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int 
 // planes (3, B, Tp, C) bf16 with hl leading halo rows; reflect / replicate / zero about the T interior rows.
 __global__ void __launch_bounds__(256)
 halo_fill_kernel(__nv_bfloat16* __restrict__ planes, int64_t plane_stride, int T, int C, int hl, int Tp, int pad_mode) {
+  pdl_entry();
   const int b = blockIdx.y, q = blockIdx.z;
   const int nh = Tp - T;                     // halo rows in total (hl leading, the rest trailing)
   const int c8 = C / 8;                      // 16-byte chunks per row
@@ -442,7 +540,7 @@ int halo_fill(void* planes_base, int B, int T, int C, int hl, int hr, int pad_mo
   const int64_t plane_stride = (int64_t)B * Tp * C;
   const int work = (hl + hr) * (C / 8);
   dim3 grid((unsigned)cdiv64(work, 256), (unsigned)B, 3);
-  halo_fill_kernel<<<grid, 256, 0, st>>>(planes, plane_stride, T, C, hl, Tp, pad_mode);
+  launch_k(halo_fill_kernel, grid, 256, 0, st, planes, plane_stride, T, C, hl, Tp, pad_mode);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -483,7 +581,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -497,6 +595,10 @@ static const CtcEnv& ctc_env() {
     e.margin = ge ? atof(ge) : 0.85;
     e.pair_mode = pe ? atoi(pe) : 1;
     e.swb64 = se && se[0] == '1';
+    const char* he = getenv("MEGATTS2_TC_HALO");          // 0: every tap re-loads its activation tile (the plain form)
+    const char* be = getenv("MEGATTS2_TC_HALO_BO");       // 1: base-offset field set in the row-shifted descriptors (diagnostics)
+    e.halo = !(he && he[0] == '0');
+    e.halo_bo = be ? atoi(be) : 0;
     return e;
   }();
   return env;
@@ -560,18 +662,19 @@ static int cmap_get(const void* p, uint64_t d0, uint64_t d1, uint64_t d2, uint32
   return 0;
 }
 
-template <int BN, int SWB, int PAIR, int NP>
+template <int BN, int SWB, int PAIR, int NP, int HALO = 0>
 static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStream_t st) {
-  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP>;
+  using Cfg = ConvTcCfg<BN, SWB, PAIR, NP, HALO>;
   // one bit per instantiation in the per-device table (the max-dynamic-shared-memory attribute is per device)
-  constexpr int slot = (BN == 128 ? 0 : BN == 64 ? 1 : 2) + 3 * (SWB == 128 ? 0 : 1) + 6 * PAIR + 12 * (NP == 3 ? 0 : 1);
+  constexpr int slot = HALO ? 24 + (BN == 64 ? 0 : 1) + 2 * (NP == 3 ? 0 : 1)
+                            : (BN == 128 ? 0 : BN == 64 ? 1 : 2) + 3 * (SWB == 128 ? 0 : 1) + 6 * PAIR + 12 * (NP == 3 ? 0 : 1);
   static_assert(slot < 32, "attribute slots");
   const int dev = cur_device();
   const int sms = cur_device_sms();
   if (!(g_dev[dev].attr_done & (1u << slot))) {
     std::lock_guard<std::mutex> lk(g_ctc_mu);
     cudaError_t e =
-        cudaFuncSetAttribute(conv_tc_kernel<BN, SWB, PAIR, NP>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
+        cudaFuncSetAttribute(conv_tc_kernel<BN, SWB, PAIR, NP, HALO>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "conv_tc", (long long)e);
     g_dev[dev].attr_done |= (1u << slot);
   }
@@ -583,15 +686,17 @@ static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStrea
     cfg.blockDim = dim3(384);
     cfg.dynamicSmemBytes = Cfg::SMEM;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at; cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SWB, PAIR, NP>, maps, a);
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<BN, SWB, PAIR, NP, HALO>, maps, a);
     if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cluster launch failed: %lld", "conv_tc", (long long)e);
   } else {
     const int grid = (int)(tiles < sms ? tiles : sms);
-    conv_tc_kernel<BN, SWB, PAIR, NP><<<grid, 384, Cfg::SMEM, st>>>(maps, a);
+    launch_k(conv_tc_kernel<BN, SWB, PAIR, NP, HALO>, grid, 384, Cfg::SMEM, st, maps, a);
   }
   MTTS_CHECK_LAUNCH();
   return 0;
@@ -646,7 +751,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
   if (!p.tc_presplit) {
     const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
-    split_pad_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
+    launch_k(split_pad_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
                                                                    p.pad_mode, p.pre_act, p.pre_slope, planes, plane_stride,
                                                                    total4, fmt, ovf);
     MTTS_CHECK_LAUNCH();
@@ -700,9 +805,13 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
     if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs
   }
   const int b_rows = pair ? BN / 2 : BN;
+  // halo form: one K-slab per tap (Cin <= SWB / 2), the activation tile + halo fits the 192-row buffer
+  const bool halo_form = env.halo && !pair && splits == 1 && p.k > 1 && p.Cin <= SWB / 2 && halo + 128 <= CTC_HALO_ROWS &&
+                         ((SWB == 64 && BN == 32) || (SWB == 128 && BN == 64)) && p.Cout == BN;
   ConvTcMaps maps;
   for (int q = 0; q < np; ++q) {
-    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2, 128, SWB, fmt, &maps.a[q]));
+    MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2,
+                      halo_form ? 128 + halo : 128, SWB, fmt, &maps.a[q]));
     MTTS_TRY(cmap_get((const __nv_bfloat16*)p.w_tc + (int64_t)q * p.k * p.Cout * p.Cin, (uint64_t)p.Cin,
                       (uint64_t)p.k * p.Cout, 0, SWB / 2, b_rows, SWB, fmt, &maps.b[q]));
   }
@@ -716,11 +825,15 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
-  a.fmt = fmt; a.ovf = ovf;
+  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo;
+  if (halo_form) {
+    if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 0, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 0, 3, 1>(maps, a, st);
+    return np == 2 ? conv_tc_launch<64, 128, 0, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 0, 3, 1>(maps, a, st);
+  }
   if (splits > 1) {
     MTTS_TRY(np == 2 ? (conv_tc_launch<128, 128, 0, 2>(maps, a, st)) : (conv_tc_launch<128, 128, 0, 3>(maps, a, st)));
     const int64_t total4 = (int64_t)p.B * p.Tout * p.Cout / 4;
-    tc_splitk_reduce_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(a, total4);
+    launch_k(tc_splitk_reduce_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, a, total4);
     MTTS_CHECK_LAUNCH();
     return 0;
   }
@@ -734,7 +847,7 @@ int split_planes(const float* x, int ldx, int64_t rows, int C, void* planes, int
   if (rows <= 0) return 0;
   MTTS_REQUIRE(rows < (int64_t)1 << 31, "too many rows");
   const int64_t total4 = rows * C / 4;
-  split_pad_kernel<<<(unsigned)cdiv64(total4, 256), 256, 0, st>>>(x, 0, ldx, (int)rows, C, 0, (int)rows, MTTS_PAD_ZERO, MTTS_ACT_NONE, 0.f,
+  launch_k(split_pad_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, x, 0, ldx, (int)rows, C, 0, (int)rows, MTTS_PAD_ZERO, MTTS_ACT_NONE, 0.f,
                                                                  reinterpret_cast<__nv_bfloat16*>(planes), rows * (int64_t)C, total4,
                                                                  fmt, tc_ovf_ptr());
   MTTS_CHECK_LAUNCH();

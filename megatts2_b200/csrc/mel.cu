@@ -21,6 +21,7 @@ constexpr int MEL_MAGP = 520;
 __device__ float2 g_tw1024[1024];   // exp(-2*pi*i*k/1024), filled once per process in fp64
 
 __global__ void mel_init_twiddle_kernel() {
+  pdl_entry();
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < 1024) {
     double s, c;
@@ -65,6 +66,7 @@ mel_kernel(const float* __restrict__ wav, int64_t wav_sb, int L_max, const int32
            const float* __restrict__ fb_w, const int32_t* __restrict__ fb_off, const int32_t* __restrict__ fb_start,
            int n_mels, float clamp_min, float* __restrict__ out, int64_t out_sb, int64_t out_sm, int64_t out_sf,
            int vec_ok) {
+  pdl_entry();
   constexpr int SPAN = MEL_NFFT + (MEL_FPB - 1) * MEL_HOP;   // 2816
   extern __shared__ __align__(16) float smem[];
   float* xs = smem;                                  // [SPAN]
@@ -272,7 +274,7 @@ int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const int32_
     if (!g_mel_ready[dev]) {
       cudaError_t e = cudaFuncSetAttribute(mel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "mel", (long long)e);
-      mel_init_twiddle_kernel<<<4, 256, 0, st>>>();
+      launch_k(mel_init_twiddle_kernel, 4, 256, 0, st);
       MTTS_CHECK_LAUNCH();
       cudaStreamSynchronize(st);   // one-time table init only; never on the steady-state path
       g_mel_ready[dev] = true;
@@ -282,7 +284,7 @@ int mel_spectrogram(const float* wav, int64_t wav_sb, int B, int L, const int32_
   for (int b0 = 0; b0 < B; b0 += 65535) {
     const int nb = (B - b0 < 65535) ? (B - b0) : 65535;
     dim3 grid((unsigned)cdiv64(F, MEL_FPB), (unsigned)nb);
-    mel_kernel<<<grid, MEL_FPB * 32, smem, st>>>(wav + (int64_t)b0 * wav_sb, wav_sb, L, lens ? lens + b0 : nullptr, window, fb_w,
+    launch_k(mel_kernel, grid, MEL_FPB * 32, smem, st, wav + (int64_t)b0 * wav_sb, wav_sb, L, lens ? lens + b0 : nullptr, window, fb_w,
                                                fb_off, fb_start, n_mels, clamp_min, out + (int64_t)b0 * out_sb, out_sb, out_sm,
                                                out_sf, vec_ok);
     MTTS_CHECK_LAUNCH();

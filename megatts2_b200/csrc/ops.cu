@@ -16,6 +16,7 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(const float* x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                  const float* res, int ldr, float* y, int ldy, int64_t rows, int C, float eps,
                  int post_act, int accumulate, int vec, const PlanesOut po) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -87,6 +88,7 @@ __global__ void __launch_bounds__(256)
 layernorm_reg_kernel(const float* x, int ldx, const float* __restrict__ gamma, const float* __restrict__ beta,
                      const float* res, int ldr, float* y, int ldy, int64_t rows, float eps, int post_act,
                      int accumulate, const PlanesOut po) {
+  pdl_entry();
   constexpr int C = 128 * NV;
   const int lane = threadIdx.x & 31;
   const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -150,14 +152,14 @@ int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta,
   const int wpb = 8;
   const unsigned grid = (unsigned)cdiv64(rows, wpb);
 #define MTTS_LN_REG(NV)                                                                                          \
-  layernorm_reg_kernel<NV><<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy, rows, eps, post_act, \
+  launch_k(layernorm_reg_kernel<NV>, grid, wpb * 32, 0, st, x, ldx, gamma, beta, res, ldr, y, ldy, rows, eps, post_act, \
                                                       accumulate, po)
   if (vec && C == 1024) MTTS_LN_REG(8);
   else if (vec && C == 768) MTTS_LN_REG(6);
   else if (vec && C == 512) MTTS_LN_REG(4);
   else if (vec && C == 384) MTTS_LN_REG(3);
   else
-    layernorm_kernel<<<grid, wpb * 32, 0, st>>>(x, ldx, gamma, beta, res, ldr, y, ldy, rows, C, eps, post_act,
+    launch_k(layernorm_kernel, grid, wpb * 32, 0, st, x, ldx, gamma, beta, res, ldr, y, ldy, rows, C, eps, post_act,
                                                 accumulate, vec, po);
 #undef MTTS_LN_REG
   MTTS_CHECK_LAUNCH();
@@ -181,6 +183,7 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
 // K and V are read once per (b, h).
 template <int NI, int RW, int NW, int KPL>
 __global__ void __launch_bounds__(NW * 32) attn_kernel(const mtts_attn_params p, const int vec, int32_t* ovf) {
+  pdl_entry();
   constexpr int DH = 32 * NI;
   constexpr int BQ = RW * NW, BKV = 32 * KPL, NT = NW * 32;
   extern __shared__ __align__(16) float sm[];
@@ -375,7 +378,7 @@ static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   const int vec = al(p.q) && al(p.k) && al(p.v) && p.q_st % 4 == 0 && p.k_st % 4 == 0 && p.v_st % 4 == 0 &&
                   p.q_sb % 4 == 0 && p.k_sb % 4 == 0 && p.v_sb % 4 == 0;
   dim3 grid((unsigned)cdiv64(p.Tq, BQ), (unsigned)p.H, (unsigned)p.B);
-  attn_kernel<NI, RW, NW, KPL><<<grid, NW * 32, smem, st>>>(p, vec, p.o_planes ? tc_ovf_ptr() : nullptr);
+  launch_k(attn_kernel<NI, RW, NW, KPL>, grid, NW * 32, smem, st, p, vec, p.o_planes ? tc_ovf_ptr() : nullptr);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -386,14 +389,17 @@ int attention(const mtts_attn_params& p, cudaStream_t st) {
   MTTS_REQUIRE(p.B >= 0 && p.H > 0 && p.Tq >= 0 && p.Tk > 0, "bad dims");
   MTTS_REQUIRE(p.H <= 65535 && p.B <= 65535, "grid too large");
   if (p.B == 0 || p.Tq == 0) return 0;
-  // tensor-core path (attn_tc.cu): the head dims of the AR stacks once the sequence feeds a 128-row MMA reasonably
+  // tensor-core path (attn_tc.cu): the head dims of the AR stacks once a sequence has more than 64 queries.  Measured at
+  // the C4 step shapes (Tq = Tk <= 64, profiles/r2c_attention_tc_ab.md) the phase-serialised tensor-core kernel is 1.5x
+  // SLOWER than this fp32 kernel (58 vs 38 us per launch: the problem is 64 x 64 x 64 per head, all latency), so the AR
+  // steps of the benchmark stay here; longer sequences (teacher-forced forwards, config C3) go to the tensor cores.
   // (MEGATTS2_ATTN_TC = 0 disables it, MEGATTS2_ATTN_TC_MIN sets the minimum Tq; read once per process)
   {
     static const int tc_min = [] {
       const char* e = getenv("MEGATTS2_ATTN_TC");
       if (e && e[0] == '0') return 1 << 30;
       const char* m = getenv("MEGATTS2_ATTN_TC_MIN");
-      return m ? atoi(m) : 16;
+      return m ? atoi(m) : 65;
     }();
     if (p.Tq >= tc_min && attention_tc_eligible(p)) return attention_tc(p, st);
   }
@@ -434,6 +440,7 @@ template <int CH>   // D = 128 * CH
 __global__ void __launch_bounds__(256)
 vq_argmin_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ embed, int64_t N, int K,
                  int64_t* __restrict__ idx) {
+  pdl_entry();
   constexpr int R = 8, D = 128 * CH;
   __shared__ float sd[8][R];
   __shared__ int sk[8][R];
@@ -500,9 +507,9 @@ int vq_argmin(const float* x, int ldx, const float* embed, int64_t N, int D, int
   if (N <= 0) return 0;
   const unsigned grid = (unsigned)cdiv64(N, 8);
   switch (D) {
-    case 128: vq_argmin_kernel<1><<<grid, 256, 0, st>>>(x, ldx, embed, N, K, idx); break;
-    case 256: vq_argmin_kernel<2><<<grid, 256, 0, st>>>(x, ldx, embed, N, K, idx); break;
-    case 512: vq_argmin_kernel<4><<<grid, 256, 0, st>>>(x, ldx, embed, N, K, idx); break;
+    case 128: launch_k(vq_argmin_kernel<1>, grid, 256, 0, st, x, ldx, embed, N, K, idx); break;
+    case 256: launch_k(vq_argmin_kernel<2>, grid, 256, 0, st, x, ldx, embed, N, K, idx); break;
+    case 512: launch_k(vq_argmin_kernel<4>, grid, 256, 0, st, x, ldx, embed, N, K, idx); break;
     default: return fail(MTTS_ERR_UNSUPPORTED, "%s: codebook dim %lld not in {128,256,512}", "vq_argmin", D);
   }
   MTTS_CHECK_LAUNCH();
@@ -512,6 +519,7 @@ int vq_argmin(const float* x, int ldx, const float* embed, int64_t N, int D, int
 __global__ void vq_gather_kernel(const int64_t* __restrict__ idx, int idx_ld, const float* __restrict__ embed, int D,
                                  int K, int T_out, int repeat, float* __restrict__ y, int64_t y_sb, int ldy,
                                  int64_t total) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int d = (int)(i % D);
@@ -528,7 +536,7 @@ int vq_gather(const int64_t* idx, int idx_ld, const float* embed, int D, int K, 
   MTTS_REQUIRE(idx && embed && y && repeat >= 1 && D > 0 && K > 0, "bad arguments");
   const int64_t total = (int64_t)B * T_out * D;
   if (total <= 0) return 0;
-  vq_gather_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(idx, idx_ld, embed, D, K, T_out, repeat, y, y_sb, ldy, total);
+  launch_k(vq_gather_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, idx, idx_ld, embed, D, K, T_out, repeat, y, y_sb, ldy, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -536,6 +544,7 @@ int vq_gather(const int64_t* idx, int idx_ld, const float* embed, int D, int K, 
 // ------------------------------------------------------------------------------------------
 __global__ void maxpool_time_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, float* __restrict__ y,
                                     int64_t y_sb, int ldy, int T, int To, int C, int k, int64_t total) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int c = (int)(i % C);
@@ -557,7 +566,7 @@ int maxpool_time(const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb, 
   const int To = (T + k - 1) / k;
   const int64_t total = (int64_t)B * To * C;
   if (total <= 0) return 0;
-  maxpool_time_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(x, x_sb, ldx, y, y_sb, ldy, T, To, C, k, total);
+  launch_k(maxpool_time_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, x, x_sb, ldx, y, y_sb, ldy, T, To, C, k, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -565,6 +574,7 @@ int maxpool_time(const float* x, int64_t x_sb, int ldx, float* y, int64_t y_sb, 
 __global__ void embed_pe_kernel(const int64_t* __restrict__ ids, int ids_ld, const float* __restrict__ table,
                                 int vocab, int D, const float* __restrict__ pe, float alpha, int pe_offset, int T,
                                 float* __restrict__ y, int64_t y_sb, int ldy, int64_t total) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int d = (int)(i % D);
@@ -583,13 +593,14 @@ int embed_pe(const int64_t* ids, int ids_ld, const float* table, int vocab, int 
   MTTS_REQUIRE(ids && table && y && D > 0 && vocab > 0, "bad arguments");
   const int64_t total = (int64_t)B * T * D;
   if (total <= 0) return 0;
-  embed_pe_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(ids, ids_ld, table, vocab, D, pe, alpha, pe_offset, T, y, y_sb, ldy, total);
+  launch_k(embed_pe_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, ids, ids_ld, table, vocab, D, pe, alpha, pe_offset, T, y, y_sb, ldy, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void add_pe_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, const float* __restrict__ pe,
                               float alpha, int T, int D, float* __restrict__ y, int64_t y_sb, int ldy, int64_t total) {
+  pdl_entry();
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   const int d = (int)(i % D);
@@ -605,7 +616,7 @@ int add_pe(const float* x, int64_t x_sb, int ldx, const float* pe, float alpha, 
   MTTS_REQUIRE(x && pe && y && D > 0, "bad arguments");
   const int64_t total = (int64_t)B * T * D;
   if (total <= 0) return 0;
-  add_pe_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(x, x_sb, ldx, pe, alpha, T, D, y, y_sb, ldy, total);
+  launch_k(add_pe_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, x, x_sb, ldx, pe, alpha, T, D, y, y_sb, ldy, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -616,6 +627,7 @@ __global__ void __launch_bounds__(256)
 length_regulate_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, const int32_t* __restrict__ dur, int dur_ld,
                        int Tp, int D, int L_out, float* __restrict__ y, int64_t y_sb, int ldy,
                        int32_t* __restrict__ totals) {
+  pdl_entry();
   extern __shared__ int cum[];   // Tp + 1
   const int b = blockIdx.y;
   if (threadIdx.x == 0) {
@@ -655,7 +667,7 @@ int length_regulate(const float* x, int64_t x_sb, int ldx, const int32_t* dur, i
   if (B == 0) return 0;
   MTTS_REQUIRE(y || L_out == 0, "null output");
   dim3 grid((unsigned)(L_out > 0 ? cdiv64(L_out, 32) : 1), (unsigned)B);
-  length_regulate_kernel<<<grid, 256, (Tp + 1) * sizeof(int), st>>>(x, x_sb, ldx, dur, dur_ld, Tp, D, L_out, y, y_sb, ldy, totals);
+  launch_k(length_regulate_kernel, grid, 256, (Tp + 1) * sizeof(int), st, x, x_sb, ldx, dur, dur_ld, Tp, D, L_out, y, y_sb, ldy, totals);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -665,6 +677,7 @@ int length_regulate(const float* x, int64_t x_sb, int ldx, const int32_t* dur, i
 __global__ void __launch_bounds__(256)
 copy_strided_kernel(const float* __restrict__ x, int64_t x_sb, int64_t x_st, int64_t x_sc, float* __restrict__ y,
                     int64_t y_sb, int64_t y_st, int64_t y_sc, int T, int C, int pad_rep) {
+  pdl_entry();
   __shared__ float tile[32][33];
   const int b = blockIdx.z;
   const int t0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
@@ -695,12 +708,13 @@ int copy_strided(const float* x, int64_t x_sb, int64_t x_st, int64_t x_sc, float
   if (B <= 0 || T <= 0 || C <= 0) return 0;
   MTTS_REQUIRE(B <= 65535 && cdiv64(C, 32) <= 65535, "grid too large");
   dim3 grid((unsigned)cdiv64(T + 2 * pad_rep, 32), (unsigned)cdiv64(C, 32), (unsigned)B);
-  copy_strided_kernel<<<grid, 256, 0, st>>>(x, x_sb, x_st, x_sc, y, y_sb, y_st, y_sc, T, C, pad_rep);
+  launch_k(copy_strided_kernel, grid, 256, 0, st, x, x_sb, x_st, x_sc, y, y_sb, y_st, y_sc, T, C, pad_rep);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void mask_tail_kernel(float* __restrict__ x, int rows, int L, const int32_t* __restrict__ keep) {
+  pdl_entry();
   const int b = blockIdx.z, r = blockIdx.y;
   const int k0 = max(keep[b], 0);
   float* xr = x + ((int64_t)b * rows + r) * L;
@@ -711,7 +725,7 @@ int mask_tail(float* x, int B, int rows, int L, const int32_t* keep, cudaStream_
   if (B == 0 || rows == 0 || L == 0) return 0;
   MTTS_REQUIRE(B <= 65535 && rows <= 65535, "grid too large");
   dim3 grid((unsigned)(cdiv64(L, 1024) < 64 ? cdiv64(L, 1024) : 64), (unsigned)rows, (unsigned)B);
-  mask_tail_kernel<<<grid, 256, 0, st>>>(x, rows, L, keep);
+  launch_k(mask_tail_kernel, grid, 256, 0, st, x, rows, L, keep);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -725,6 +739,7 @@ __global__ void plm_build_input_kernel(const float* __restrict__ tc, int64_t tc_
                                        const float* __restrict__ emb, int vq_dim, int vocab,
                                        const float* __restrict__ pe, float alpha, int S, float* __restrict__ X,
                                        int64_t total) {
+  pdl_entry();
   const int D = tc_dim + vq_dim;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -748,7 +763,7 @@ int plm_build_input(const float* tc, int64_t tc_sb, int tc_ld, int tc_dim, const
                     cudaStream_t st) {
   const int64_t total = (int64_t)B * S * (tc_dim + vq_dim);
   if (total <= 0) return 0;
-  plm_build_input_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(tc, tc_sb, tc_ld, tc_dim, codes, codes_ld, emb, vq_dim, vocab, pe, alpha, S, X, total);
+  launch_k(plm_build_input_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, tc, tc_sb, tc_ld, tc_dim, codes, codes_ld, emb, vq_dim, vocab, pe, alpha, S, X, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -757,6 +772,7 @@ int plm_build_input(const float* tc, int64_t tc_sb, int tc_ld, int tc_dim, const
 // writes out_a[row*lda] and (optionally) out_b[row*ldb].
 __global__ void argmax_rows_kernel(const float* __restrict__ x, int64_t ldx, int V, int rows, int64_t* out_a,
                                    int64_t lda, int64_t* out_b, int64_t ldb) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= rows) return;
@@ -783,28 +799,30 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, int64_t ldx, int
 int argmax_rows(const float* x, int64_t ldx, int V, int rows, int64_t* out_a, int64_t lda, int64_t* out_b, int64_t ldb,
                 cudaStream_t st) {
   if (rows <= 0) return 0;
-  argmax_rows_kernel<<<(unsigned)cdiv64(rows, 4), 128, 0, st>>>(x, ldx, V, rows, out_a, lda, out_b, ldb);
+  launch_k(argmax_rows_kernel, (unsigned)cdiv64(rows, 4), 128, 0, st, x, ldx, V, rows, out_a, lda, out_b, ldb);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
 
 __global__ void fill_i64_kernel(int64_t* p, int64_t stride, int n, int64_t v) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[(int64_t)i * stride] = v;
 }
 int fill_i64(int64_t* p, int64_t stride, int n, int64_t v, cudaStream_t st) {
   if (n <= 0) return 0;
-  fill_i64_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(p, stride, n, v);
+  launch_k(fill_i64_kernel, (unsigned)cdiv64(n, 256), 256, 0, st, p, stride, n, v);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
 __global__ void fill_f32_kernel(float* p, int64_t stride, int n, float v) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[(int64_t)i * stride] = v;
 }
 int fill_f32(float* p, int64_t stride, int n, float v, cudaStream_t st) {
   if (n <= 0) return 0;
-  fill_f32_kernel<<<(unsigned)cdiv64(n, 256), 256, 0, st>>>(p, stride, n, v);
+  launch_k(fill_f32_kernel, (unsigned)cdiv64(n, 256), 256, 0, st, p, stride, n, v);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -814,6 +832,7 @@ __global__ void adm_build_input_kernel(const float* __restrict__ tc_emb, int64_t
                                        const float* __restrict__ praw, int p_ld, const float* __restrict__ w_dt,
                                        int emb_dim, const float* __restrict__ pe, float alpha, int S,
                                        float* __restrict__ X, int64_t total) {
+  pdl_entry();
   const int D = tc_emb_dim + emb_dim;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
@@ -832,7 +851,7 @@ int adm_build_input(const float* tc_emb, int64_t te_sb, int te_ld, int tc_emb_di
                     cudaStream_t st) {
   const int64_t total = (int64_t)B * S * (tc_emb_dim + emb_dim);
   if (total <= 0) return 0;
-  adm_build_input_kernel<<<(unsigned)cdiv64(total, 256), 256, 0, st>>>(tc_emb, te_sb, te_ld, tc_emb_dim, praw, p_ld, w_dt, emb_dim, pe, alpha, S, X, total);
+  launch_k(adm_build_input_kernel, (unsigned)cdiv64(total, 256), 256, 0, st, tc_emb, te_sb, te_ld, tc_emb_dim, praw, p_ld, w_dt, emb_dim, pe, alpha, S, X, total);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -840,6 +859,7 @@ int adm_build_input(const float* tc_emb, int64_t te_sb, int te_ld, int tc_emb_di
 // ADM readout (models/megatts2.py:272-273): p[b, s_next] = x_last[b,:] . w_predict ; one warp per b
 __global__ void adm_readout_kernel(const float* __restrict__ xl, int D, const float* __restrict__ w, int B,
                                    float* __restrict__ praw, int p_ld, int s_next) {
+  pdl_entry();
   const int lane = threadIdx.x & 31;
   const int b = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (b >= B) return;
@@ -850,7 +870,7 @@ __global__ void adm_readout_kernel(const float* __restrict__ xl, int D, const fl
 }
 int adm_readout(const float* xl, int D, const float* w, int B, float* praw, int p_ld, int s_next, cudaStream_t st) {
   if (B <= 0) return 0;
-  adm_readout_kernel<<<(unsigned)cdiv64(B, 4), 128, 0, st>>>(xl, D, w, B, praw, p_ld, s_next);
+  launch_k(adm_readout_kernel, (unsigned)cdiv64(B, 4), 128, 0, st, xl, D, w, B, praw, p_ld, s_next);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -858,6 +878,7 @@ int adm_readout(const float* xl, int D, const float* w, int B, float* praw, int 
 // (p + 0.5).to(int32).clamp(1, 128)  (models/megatts2.py:275); praw row b holds [0, p_1..p_T]
 __global__ void adm_finalize_kernel(const float* __restrict__ praw, int p_ld, int B, int T, int32_t* __restrict__ dur,
                                     float* __restrict__ raw_out) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * T) return;
   const int b = i / T, t = i - b * T;
@@ -869,7 +890,7 @@ __global__ void adm_finalize_kernel(const float* __restrict__ praw, int p_ld, in
 }
 int adm_finalize(const float* praw, int p_ld, int B, int T, int32_t* dur, float* raw_out, cudaStream_t st) {
   if (B * T <= 0) return 0;
-  adm_finalize_kernel<<<(unsigned)cdiv64((int64_t)B * T, 256), 256, 0, st>>>(praw, p_ld, B, T, dur, raw_out);
+  launch_k(adm_finalize_kernel, (unsigned)cdiv64((int64_t)B * T, 256), 256, 0, st, praw, p_ld, B, T, dur, raw_out);
   MTTS_CHECK_LAUNCH();
   return 0;
 }

@@ -33,6 +33,7 @@ __device__ __forceinline__ int map_row(int ti, int len, int mode) {
 template <int BM, int BN, int TM, int TN>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN), ((BM / TM) * (BN / TN) <= 256 ? 2 : 1))
 tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
+  pdl_entry();
   constexpr int BK = 16;
   constexpr int NT = (BM / TM) * (BN / TN);
   constexpr int AP = BM + 4;
@@ -257,6 +258,7 @@ tapconv_kernel(const mtts_conv_params p, const ConvFlags fl) {
 // memory.  A 128x32 GEMM tile would waste 31/32 of its columns here.
 __global__ void __launch_bounds__(256)
 conv_cout1_kernel(const mtts_conv_params p) {
+  pdl_entry();
   extern __shared__ __align__(16) float wsm[];       // [k][Cin]
   for (int i = threadIdx.x; i < p.k * p.Cin; i += 256) wsm[i] = __ldg(p.w + i);   // packed (k, Cin, 1)
   __syncthreads();
@@ -294,6 +296,7 @@ conv_cout1_kernel(const mtts_conv_params p) {
 // split-K second pass: fixed-order sum of the partials (deterministic), then the usual epilogue
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const mtts_conv_params p, const float* __restrict__ partial, int splits) {
+  pdl_entry();
   const int64_t M = (int64_t)p.B * p.Tout;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= M * p.Cout) return;
@@ -315,7 +318,7 @@ template <int BM, int BN, int TM, int TN>
 static int launch_cfg(const mtts_conv_params& p, const ConvFlags& fl, cudaStream_t st) {
   const int64_t M = (int64_t)p.B * p.Tout;
   dim3 grid((unsigned)cdiv64(M, BM), (unsigned)cdiv64(p.Cout, BN));
-  tapconv_kernel<BM, BN, TM, TN><<<grid, (BM / TM) * (BN / TN), 0, st>>>(p, fl);
+  launch_k(tapconv_kernel<BM, BN, TM, TN>, grid, (BM / TM) * (BN / TN), 0, st, p, fl);
   MTTS_CHECK_LAUNCH();
   return 0;
 }
@@ -340,7 +343,7 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st) {
              (p.out_shift % 4 == 0) && (p.y_batch_elems % 4 == 0) &&
              (!p.res || ((p.ldr % 4 == 0) && (p.res_batch_stride % 4 == 0) && al16(p.res)));
   if (p.Cout == 1 && p.out_shift == 0 && fl.vec_a && p.k * p.Cin <= 8192 && M >= 4096) {
-    conv_cout1_kernel<<<(unsigned)cdiv64(M, 256), 256, (size_t)p.k * p.Cin * sizeof(float), st>>>(p);
+    launch_k(conv_cout1_kernel, (unsigned)cdiv64(M, 256), 256, (size_t)p.k * p.Cin * sizeof(float), st, p);
     MTTS_CHECK_LAUNCH();
     return 0;
   }
@@ -362,9 +365,9 @@ int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st) {
         splits = (nk + fl.kk_per_split - 1) / fl.kk_per_split;
         fl.partial = reinterpret_cast<float*>((((uintptr_t)p.tc_scratch) + 255) & ~(uintptr_t)255);
         dim3 grid((unsigned)cdiv64(M, 64), (unsigned)cdiv64(p.Cout, 64), (unsigned)splits);
-        tapconv_kernel<64, 64, 4, 4><<<grid, 256, 0, st>>>(p, fl);
+        launch_k(tapconv_kernel<64, 64, 4, 4>, grid, 256, 0, st, p, fl);
         MTTS_CHECK_LAUNCH();
-        splitk_reduce_kernel<<<(unsigned)cdiv64(M * p.Cout, 256), 256, 0, st>>>(p, fl.partial, splits);
+        launch_k(splitk_reduce_kernel, (unsigned)cdiv64(M * p.Cout, 256), 256, 0, st, p, fl.partial, splits);
         MTTS_CHECK_LAUNCH();
         return 0;
       }
