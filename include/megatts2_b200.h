@@ -213,6 +213,23 @@ int mtts_copy_strided_f32(const float* x, int64_t x_sb, int64_t x_st, int64_t x_
                           float* y, int64_t y_sb, int64_t y_st, int64_t y_sc,
                           int32_t B, int32_t T, int32_t C, int32_t pad_rep, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Audio front / back ends of Megatts.forward on the device.
+ *
+ * mtts_resample_f32 - librosa.load(path, sr=16000) at models/megatts2.py:335 (and prepare_ds.py:113), the resampling
+ * part: band-limited polyphase FIR, y[i*up + p] = sum_k xpad[i*down + k] * h[p][k] with xpad = x preceded by `width`
+ * zeros; h is the (up, taps) filter table of torchaudio.functional.resample (built on the host in fp64:
+ * megatts2_b200/audio.py).  x (B, L_in) with optional per-clip lengths; y (B, L_out), samples past lens_out[b] are zero.
+ * mtts_peak_normalize_f32 - librosa.util.normalize(y) (:336): x[b] /= max|x[b]| in place (unchanged if the peak is below
+ * FLT_MIN); scratch: B x 4 bytes.
+ * mtts_pcm16_f32 - the integer encoding of the wav writer behind torchaudio.save (:375): round-to-nearest of x * 32768,
+ * saturated. */
+int mtts_resample_f32(const float* x, int64_t x_sb, int32_t B, int32_t L_in, const int32_t* lens_in, const float* h,
+                      int32_t up, int32_t down, int32_t width, int32_t taps, float* y, int64_t y_sb, int32_t L_out,
+                      const int32_t* lens_out, void* stream);
+int mtts_peak_normalize_f32(float* x, int64_t x_sb, int32_t B, int32_t L, const int32_t* lens, void* scratch, void* stream);
+int mtts_pcm16_f32(const float* x, int64_t n, int16_t* out, void* stream);
+
 /* x (B, rows, L) contiguous: x[b, r, keep[b]:] = 0 in place - speechbrain HIFIGAN.mask_noise behind
  * decode_batch(mel, mel_lens, hop_len) (reference call site models/megatts2.py:370). */
 int mtts_mask_tail_f32(float* x, int32_t B, int32_t rows, int32_t L, const int32_t* keep, void* stream);

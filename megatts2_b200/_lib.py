@@ -119,6 +119,9 @@ SIGNATURES = {
     "mtts_split_planes_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp]),
     "mtts_tc_overflow_bind": (C.c_int, [vp]),
     "mtts_mask_tail_f32": (C.c_int, [vp, i32, i32, i32, vp, vp]),
+    "mtts_resample_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, vp, i64, i32, vp, vp]),
+    "mtts_peak_normalize_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, vp]),
+    "mtts_pcm16_f32": (C.c_int, [vp, i64, vp, vp]),
     "mtts_layernorm_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, f32, i32, i32, vp]),
     "mtts_attention_f32": (C.c_int, [C.POINTER(AttnParams), vp]),
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),

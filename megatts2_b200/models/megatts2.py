@@ -567,25 +567,32 @@ class Megatts(nn.Module):
                     out[i] = wav[j, 0, :lens[j]]
         return out
 
-    def forward(self, wavs_dir: str, text: str):
-        """Reference signature (models/megatts2.py:325-375): prompt wavs + text -> writes test.wav."""
+    def forward(self, wavs_dir: str, text: str, out_path: str = 'test.wav'):
+        """Reference signature (models/megatts2.py:325-375): prompt wavs + text -> writes test.wav.  The audio side
+        (decode, resample to 16 kHz, peak normalisation, mel, wav writing) runs through megatts2_b200.audio on the device
+        (SURVEY.md 8f-3); the text side needs the reference's host-side G2P (TextTokenizer / TokensCollector - out of the
+        hot path) to be importable."""
+        from .. import audio
         try:
-            import librosa
-            import torchaudio
             from modules.tokenizer import TextTokenizer          # the reference's host-side G2P
             from modules.datamodule import TokensCollector
-        except Exception as e:   # pragma: no cover - host front end is outside the hot path
-            raise L.MttsError("Megatts.forward needs the reference's host-side text/audio front end "
-                              f"(librosa, G2P, TokensCollector): {e}; use synthesize() with tensors") from e
+        except Exception as e:   # pragma: no cover - host text front end is outside the hot path
+            raise L.MttsError("Megatts.forward needs the reference's host-side text front end (G2P, TokensCollector): "
+                              f"{e}; use synthesize() with phone tensors") from e
         dev = next(self.parameters()).device
-        mels, mels_prompt = [], None
-        for wav in glob.glob(f'{wavs_dir}/*.wav'):
-            y = torch.from_numpy(librosa.util.normalize(librosa.load(wav, sr=HIFIGAN_SR)[0])).to(dev)
-            m = extract_mel_spec(y.unsqueeze(0), frames_major=True)[0]
-            mels.append(m)
-            mels_prompt = m if mels_prompt is None else mels_prompt
-        mels = torch.cat(mels, 0).unsqueeze(0)
+        clips = [audio.read_wav(w) for w in glob.glob(f'{wavs_dir}/*.wav')]
+        mels, mels_prompt = self.prompt_mels(clips)
         tt, ttc = TextTokenizer(), TokensCollector(self.symbol_table)
         phone_tokens = ttc.phone2token(tt.tokenize_lty(tt.tokenize(text))).unsqueeze(0).to(dev)
-        audio = self.synthesize(phone_tokens, mels, prompt_mels=mels_prompt.unsqueeze(0))
-        torchaudio.save('test.wav', audio[0].cpu(), HIFIGAN_SR)
+        audio_out = self.synthesize(phone_tokens, mels, prompt_mels=mels_prompt)
+        audio.save_wav(out_path, audio_out[0], HIFIGAN_SR)
+
+    def prompt_mels(self, clips):
+        """The prompt loop of forward() (:333-346) for decoded clips [(float32 samples, sr)]: resample + normalise (one
+        launch per sampling rate), mel per clip, concatenated along time -> (mels (1, sum frames, 80), first clip's mel
+        (1, frames, 80))."""
+        from .. import audio
+        dev = next(self.parameters()).device
+        wav, lens = audio.load_prompts(clips, dev, HIFIGAN_SR)
+        per_clip = [extract_mel_spec(wav[i:i + 1, :n], frames_major=True)[0] for i, n in enumerate(lens.tolist())]
+        return torch.cat(per_clip, 0).unsqueeze(0), per_clip[0].unsqueeze(0)

@@ -115,3 +115,27 @@ def test_megag_forward_and_s2_latent_vs_oracle(weights_cpu):
     assert (mel.cpu() - mel_ref).abs().mean().item() < 1e-4 and (mel.cpu() - mel_ref).abs().max().item() < 1e-3
     assert float(commit.abs().max()) == 0.0 and commit.shape == commit_ref.shape
     assert abs(float(vql) - float(vql_ref)) < 1e-5 * max(1.0, float(vql_ref))
+
+
+def test_stage2_latent_dump_layout_and_values(weights_cpu, tmp_path):
+    """8f-2: megatts2_b200.latents.dump_s2_latents writes what prepare_ds.py:224-258 writes - one pickled dict per cut,
+    {'tc_latent': (1, Tp, 512) float32, 'p_code': (1, 1, ceil(Tt / 8)) int64} - bucketing equal-shape cuts into one batch;
+    values vs the oracle's batch-1 restatement of G.s2_latent."""
+    import numpy as np
+    from megatts2_b200.latents import dump_s2_latents
+    G = helpers.build_g(weights_cpu("g"), DEV)
+    g = R.SD(weights_cpu("g"))
+    items = []
+    for i, (tp, tm, tt) in enumerate([(6, 96, 40), (9, 64, 33), (6, 96, 40)]):
+        items.append((f"rec{i}", f"spk{i % 2}", torch.randint(0, 320, (tp,), generator=gen(300 + i)),
+                      torch.randn(tm, 80, generator=gen(310 + i)) * 2 - 4, torch.randn(tt, 80, generator=gen(320 + i)) * 2 - 4))
+    paths = dump_s2_latents(G, items, str(tmp_path))
+    for (rid, spk, ph, mt, mg), pth in zip(items, paths):
+        assert pth == str(tmp_path / "latents" / spk / f"{rid}.npy")
+        d = np.load(pth, allow_pickle=True).item()
+        tc_ref, _, _ = R.mrte_tc_latent(g.sub("mrte"), ph[None], mt[None], weights.G_CFG)
+        _, _, _, codes_ref, _ = R.vqpe_forward(g.sub("vqpe"), mg[None], weights.G_CFG)
+        assert d["tc_latent"].shape == (1, ph.shape[0], 512) and d["tc_latent"].dtype == np.float32
+        assert d["p_code"].shape == (1, 1, (mg.shape[0] + 7) // 8) and d["p_code"].dtype == np.int64
+        assert np.array_equal(d["p_code"], codes_ref.numpy())
+        assert np.abs(d["tc_latent"] - tc_ref.numpy()).max() < 2e-4

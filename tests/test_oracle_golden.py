@@ -3,6 +3,8 @@ REAL reference (tests/golden/*.npz, written by oracle/make_golden.py in the buil
 This is what pins the oracle; the GPU parity tests then compare the CUDA path to the oracle
 and to the same fixtures."""
 import json
+
+import numpy as np
 import os
 
 import pytest
@@ -163,3 +165,45 @@ def test_c_oracle_vq_matches_reference_fixture(golden, weights_cpu):
     mism = idx != g["idx"]
     assert bool((g["gap64"][mism] < 2e-4).all())      # only genuine fp32 near-ties may differ
     assert torch.equal(idx[:512], g["idx"][:512])
+
+
+def test_audio_front_end_restatement_vs_torchaudio():
+    """8f-3: the oracle's polyphase resampler == torchaudio.functional.resample (the published definition it restates),
+    and the product's host-built fp32 filter table is bit-identical to torchaudio's own."""
+    import math
+    import torchaudio
+    from torchaudio.functional.functional import _get_sinc_resample_kernel
+    from megatts2_b200 import audio
+    from oracle import ref_audio
+    g = torch.Generator().manual_seed(11)
+    for o, n in ((44100, 16000), (48000, 16000), (22050, 16000), (24000, 16000), (8000, 16000)):
+        x = torch.rand(7000, generator=g) * 2 - 1
+        ref = torchaudio.functional.resample(x[None], o, n, resampling_method="sinc_interp_kaiser", **ref_audio.KAISER_BEST)[0]
+        got = ref_audio.resample(x.numpy(), o, n)
+        assert got.shape == tuple(ref.shape)
+        assert np.abs(got - ref.numpy()).max() < 5e-5
+        k, w = _get_sinc_resample_kernel(o, n, math.gcd(o, n), resampling_method="sinc_interp_kaiser", **audio.KAISER_BEST)
+        up, down, width, h = audio.resample_table(o, n, **audio.KAISER_BEST)
+        assert width == w and np.array_equal(h, k[:, 0].numpy())
+    y = ref_audio.peak_normalize(np.array([0.25, -0.5, 0.125], dtype=np.float32))
+    assert np.array_equal(y, np.array([0.5, -1.0, 0.25], dtype=np.float32))
+    assert np.array_equal(ref_audio.peak_normalize(np.zeros(4, dtype=np.float32)), np.zeros(4, dtype=np.float32))
+
+
+def test_wav_framing_round_trip(tmp_path):
+    """The host half of the wav writer / reader: RIFF framing of float32 and int16 payloads, readable by the stdlib."""
+    import wave
+    from megatts2_b200 import audio
+    x = (np.random.RandomState(0).rand(1234).astype(np.float32) * 2 - 1)
+    pf = tmp_path / "f.wav"
+    pf.write_bytes(audio.wav_bytes(x, 16000, "PCM_F"))
+    y, sr = audio.read_wav(str(pf))
+    assert sr == 16000 and np.array_equal(x, y)
+    q = np.clip(np.rint(x * 32768.0), -32768, 32767).astype(np.int16)
+    pi = tmp_path / "i.wav"
+    pi.write_bytes(audio.wav_bytes(q, 22050, "PCM_S"))
+    with wave.open(str(pi)) as w:
+        assert (w.getnchannels(), w.getsampwidth(), w.getframerate(), w.getnframes()) == (1, 2, 22050, 1234)
+        assert w.readframes(1234) == q.tobytes()
+    y2, sr2 = audio.read_wav(str(pi))
+    assert sr2 == 22050 and np.array_equal(y2, q.astype(np.float32) / 32768.0)
