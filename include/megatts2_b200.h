@@ -230,6 +230,33 @@ int mtts_resample_f32(const float* x, int64_t x_sb, int32_t B, int32_t L_in, con
 int mtts_peak_normalize_f32(float* x, int64_t x_sb, int32_t B, int32_t L, const int32_t* lens, void* scratch, void* stream);
 int mtts_pcm16_f32(const float* x, int64_t n, int16_t* out, void* stream);
 
+/* ------------------------------------------------------------------------------------------
+ * Training-mode / backward kernels: what autograd needs so that MegaPLMTrainer / MegaADMTrainer
+ * .training_step (models/trainer.py:243-268, 334-355) run through the drop-in modules.  The dense contractions of the
+ * backward pass (dX = dY W, dW = dY^T X) use mtts_linear_tc_f32 / mtts_conv1d_f32 like the forward; these are the rest.
+ *
+ * mtts_bmm_f32: C[z1,z2][m,n] = alpha * sum_k A[z1,z2][m,k] * B[z1,z2][k,n] (+ C), every operand given by element strides
+ *   (transposes and (B,T,H,dh) head views are free) - the attention products Q K^T, P V and their gradients.
+ * mtts_softmax_fwd_f32: rows of S (B,H,Tq,Tk) -> P = softmax(S + mask) and Pd = P * keep (keep = dropout keep-scale or
+ *   NULL); mtts_softmax_bwd_f32: dS = P * (dPd * keep - <dPd * keep, P>)   (F.scaled_dot_product_attention with dropout,
+ *   modules/transformer.py:52-53, unfused for training).
+ * mtts_layernorm_bwd_f32: dx (rows, C) and per-CTA partials (ceil(rows / 8), 2, C) of d-gamma | d-beta
+ *   (reduce with mtts_colsum_f32).  mtts_colsum_f32: out[c] (+)= sum_r in[r*ld + c], fixed row order.
+ * mtts_relu_bwd_f32: dx = dy * (y > 0).  mtts_embedding_bwd_f32: dW[ids[r]] += dy[r] (nn.Embedding).
+ * mtts_rowdot_f32: out[r] = <a[r, :], b[r % period, :]> (d-alpha of SinePositionalEmbedding). */
+int mtts_bmm_f32(const float* a, int64_t a_s1, int64_t a_s2, int64_t a_sm, int64_t a_sk, const float* b, int64_t b_s1,
+                 int64_t b_s2, int64_t b_sk, int64_t b_sn, float* c, int64_t c_s1, int64_t c_s2, int64_t c_sm, int64_t c_sn,
+                 int32_t Z1, int32_t Z2, int32_t M, int32_t N, int32_t K, float alpha, int32_t accumulate, void* stream);
+int mtts_softmax_fwd_f32(const float* S, const float* mask, int64_t m_sb, int64_t m_sh, int64_t m_sq, int32_t B, int32_t H,
+                         int32_t Tq, int32_t Tk, const float* keep, float* P, float* Pd, void* stream);
+int mtts_softmax_bwd_f32(const float* P, const float* dPd, const float* keep, float* dS, int32_t Tk, int64_t rows, void* stream);
+int mtts_layernorm_bwd_f32(const float* x, const float* gamma, const float* dy, float* dx, float* partial, int64_t rows, int32_t C,
+                           float eps, void* stream);
+int mtts_colsum_f32(const float* in, int64_t ld, int64_t rows, int32_t C, float* out, int32_t accumulate, void* stream);
+int mtts_relu_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream);
+int mtts_embedding_bwd_f32(const int64_t* ids, const float* dy, int64_t rows, int32_t D, int32_t vocab, float* dW, void* stream);
+int mtts_rowdot_f32(const float* a, const float* b, int64_t rows, int32_t C, int32_t period, float* out, void* stream);
+
 /* x (B, rows, L) contiguous: x[b, r, keep[b]:] = 0 in place - speechbrain HIFIGAN.mask_noise behind
  * decode_batch(mel, mel_lens, hop_len) (reference call site models/megatts2.py:370). */
 int mtts_mask_tail_f32(float* x, int32_t B, int32_t rows, int32_t L, const int32_t* keep, void* stream);

@@ -122,6 +122,15 @@ SIGNATURES = {
     "mtts_resample_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, vp, i64, i32, vp, vp]),
     "mtts_peak_normalize_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, vp]),
     "mtts_pcm16_f32": (C.c_int, [vp, i64, vp, vp]),
+    "mtts_bmm_f32": (C.c_int, [vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, vp, i64, i64, i64, i64, i32, i32, i32, i32, i32,
+                               f32, i32, vp]),
+    "mtts_softmax_fwd_f32": (C.c_int, [vp, vp, i64, i64, i64, i32, i32, i32, i32, vp, vp, vp, vp]),
+    "mtts_softmax_bwd_f32": (C.c_int, [vp, vp, vp, vp, i32, i64, vp]),
+    "mtts_layernorm_bwd_f32": (C.c_int, [vp, vp, vp, vp, vp, i64, i32, f32, vp]),
+    "mtts_colsum_f32": (C.c_int, [vp, i64, i64, i32, vp, i32, vp]),
+    "mtts_relu_bwd_f32": (C.c_int, [vp, vp, vp, i64, vp]),
+    "mtts_embedding_bwd_f32": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
+    "mtts_rowdot_f32": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
     "mtts_layernorm_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, f32, i32, i32, vp]),
     "mtts_attention_f32": (C.c_int, [C.POINTER(AttnParams), vp]),
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),

@@ -15,6 +15,7 @@ import torch.nn as nn
 import yaml
 
 from .. import _lib as L
+from .. import autograd as A
 from .. import ops, pack
 from ..modules.convnet import ConvNet
 from ..modules.embedding import SinePositionalEmbedding
@@ -27,8 +28,8 @@ from ..utils.utils import instantiate_class
 
 def _eval_only(m):
     if m.training:
-        raise L.MttsError("training-mode forward is outside the synthesis path (call .eval()); "
-                          "backward kernels are a later row (SURVEY.md §8f-4)")
+        raise L.MttsError("this entry point is inference-only (call .eval()); training-mode forwards exist for MegaPLM / "
+                          "MegaADM (SURVEY.md 8f-4), the generator trainer's path (conv stacks, VQ EMA) is not built")
 
 
 class MegaG(nn.Module):
@@ -119,9 +120,13 @@ class MegaPLM(pack.PlanMixin, nn.Module):
         return self._plan
 
     def forward(self, tc_latent: torch.Tensor, p_codes: torch.Tensor, lens: torch.Tensor):
-        """Teacher-forced logits with the causal + padding mask (models/megatts2.py:148-163).
-        Forward only."""
-        _eval_only(self)
+        """Teacher-forced logits with the causal + padding mask (models/megatts2.py:148-163).  In training mode the
+        graph is built from megatts2_b200.autograd Functions (forward + backward kernels)."""
+        if self.training:
+            pc_emb = A.EmbeddingFn.apply(p_codes[:, :-1], self.pc_embedding.weight)
+            x = self.pos(torch.cat([tc_latent, pc_emb], dim=-1))
+            h = self.plm(x, lens, causal=True)
+            return A.linear(h, self.predict_layer.weight, None), p_codes[:, 1:]
         T = tc_latent.shape[1]
         dev = tc_latent.device
         x = torch.empty(tc_latent.shape[0], T, self.tc_latent_dim + self.vq_dim, dtype=torch.float32, device=dev)
@@ -219,8 +224,13 @@ class MegaADM(pack.PlanMixin, nn.Module):
         return self._plan
 
     def forward(self, tc_latents: torch.Tensor, duration_tokens: torch.Tensor, lens: torch.Tensor):
-        """Teacher-forced duration regression (models/megatts2.py:233-255).  Forward only."""
-        _eval_only(self)
+        """Teacher-forced duration regression (models/megatts2.py:233-255); training mode runs on autograd Functions."""
+        if self.training:
+            dt_emb = A.linear(duration_tokens[:, :-1].float(), self.dt_linear_emb.weight, None)
+            tc_emb = A.linear(tc_latents, self.tc_linear_emb.weight, None)
+            x = self.pos_emb(torch.cat([tc_emb, dt_emb], dim=-1))
+            h = self.adm(x, lens, causal=True)
+            return A.linear(h, self.predict_layer.weight, None)[..., 0], duration_tokens[:, 1:, 0]
         B, T, _ = tc_latents.shape
         dev = tc_latents.device
         x = torch.empty(B, T, self.tc_emb_dim + self.emb_dim, dtype=torch.float32, device=dev)

@@ -7,6 +7,7 @@ import math
 import torch
 import torch.nn as nn
 
+from .. import autograd as A
 from .. import ops
 
 
@@ -40,7 +41,8 @@ class TokenEmbedding(nn.Module):
         return self.word_embeddings.weight[index:index + 1]
 
     def forward(self, x: torch.Tensor):
-        assert not (self.training and self.dropout.p > 0), "training-mode dropout is outside the synthesis path"
+        if self.training:
+            return A.dropout(A.EmbeddingFn.apply(x, self.word_embeddings.weight), self.dropout.p, True)
         return ops.embed_pe(x, self.word_embeddings.weight.detach())
 
 
@@ -79,7 +81,9 @@ class SinePositionalEmbedding(nn.Module):
 
     def forward(self, x: torch.Tensor, offset: int = 0) -> torch.Tensor:
         assert self.x_scale == 1.0, "scale=True is not used on the synthesis path"
-        assert not (self.training and self.dropout.p > 0), "training-mode dropout is outside the synthesis path"
         self.extend_pe(x, offset)
         out = x.unsqueeze(-1) if x.ndim == 2 else x
+        if self.training:
+            y = A.SinePosFn.apply(out, self.alpha, self.pe[offset:offset + out.size(1)].contiguous())
+            return A.dropout(y, self.dropout.p, True)
         return ops.add_pe(out, self.pe[offset:offset + out.size(1)].contiguous(), self.alpha_host())

@@ -3,8 +3,9 @@ surface (modules/transformer.py:16-57, 59-102, 105-133): same ctor kwargs, attri
 state_dict keys (w_q/w_k/w_v, out_proj.0, norm1/2, ff.0/ff.2|ff.3, layers.{i}) and forward
 signatures.  The nn.Linear / nn.Conv1d / nn.LayerNorm children only HOLD parameters; the
 math runs in libmegatts2_b200 (mtts_encoder_forward_f32: LN -> packed QKV GEMM -> attention
--> out-proj + residual -> FFN, one C call for the whole stack).  Forward-only (inference);
-autograd through the kernels is a later row."""
+-> out-proj + residual -> FFN, one C call for the whole stack) in eval mode.  In TRAINING mode the
+forward is composed from megatts2_b200.autograd Functions - the same kernels plus their backward kernels, dropout
+included - so ``loss.backward()`` flows through the library (linear-FF layers: the PLM / ADM trainers)."""
 import copy
 import ctypes as C
 
@@ -12,6 +13,7 @@ import torch
 from torch import nn
 
 from .. import _lib as L
+from .. import autograd as A
 from .. import ops, pack
 from ..utils.utils import make_attn_mask
 
@@ -57,7 +59,8 @@ class MultiHeadAttention(pack.PlanMixin, nn.Module):
 
     def forward(self, q, kv=None, mask=None):
         """q (B,Tq,D), kv (B,Tk,D) or None (self-attention), additive mask broadcastable to (B,H,Tq,Tk)."""
-        _no_train_dropout(self, self.dropout)
+        if self.training:
+            return self.forward_train(q, kv, mask)
         pl = self._packed()
         D = self.qkv_dim
         if kv is None:
@@ -69,6 +72,22 @@ class MultiHeadAttention(pack.PlanMixin, nn.Module):
             kk, vv = kvp[..., :D], kvp[..., D:]
         att = ops.attention(qq, kk, vv, self.n_heads, mask)
         return ops.linear(att, pl.wo, self.out_proj[0].bias.detach())
+
+
+def _mha_forward_train(self, q, kv=None, mask=None):
+    """Training-mode MultiHeadAttention.forward (modules/transformer.py:35-57) on autograd Functions: three projections,
+    unfused attention with dropout on the probabilities (F.scaled_dot_product_attention(..., dropout_p)), out-projection,
+    nn.Dropout."""
+    src = q if kv is None else kv
+    qq = A.linear(q, self.w_q.weight, self.w_q.bias)
+    kk = A.linear(src, self.w_k.weight, self.w_k.bias)
+    vv = A.linear(src, self.w_v.weight, self.w_v.bias)
+    att = A.AttentionFn.apply(qq, kk, vv, self.n_heads, mask, float(self.dropout))
+    out = A.linear(att, self.out_proj[0].weight, self.out_proj[0].bias)
+    return A.dropout(out, self.out_proj[1].p, True)
+
+
+MultiHeadAttention.forward_train = _mha_forward_train
 
 
 class TransformerEncoderLayer(pack.PlanMixin, nn.Module):
@@ -94,7 +113,20 @@ class TransformerEncoderLayer(pack.PlanMixin, nn.Module):
         self._plan = None
 
     def forward(self, x: torch.Tensor, mask: torch.Tensor = None):
+        if self.training:
+            return self.forward_train(x, mask)
         return run_encoder(self, [self], x, mask)
+
+    def forward_train(self, x, mask=None):
+        """Training-mode layer (modules/transformer.py:88-102), linear feed-forward: x + attn(LN1(x)); x + FF(LN2(x)) with
+        FF = Linear -> ReLU -> Dropout -> Linear."""
+        if self.conv_ff:
+            raise L.MttsError("training through the conv feed-forward layers (MRTE phone encoder, generator trainer) is not "
+                              "built yet; the PLM / ADM stacks use the linear feed-forward")
+        x = x + self.attn(A.layernorm(x, self.norm1), mask=mask)
+        h = A.linear(A.layernorm(x, self.norm2), self.ff[0].weight, self.ff[0].bias, relu=True)
+        h = A.dropout(h, self.p_drop, True)
+        return x + A.linear(h, self.ff[3].weight, self.ff[3].bias)
 
 
 class TransformerEncoder(pack.PlanMixin, nn.Module):
@@ -107,6 +139,10 @@ class TransformerEncoder(pack.PlanMixin, nn.Module):
 
     def forward(self, x: torch.Tensor, x_lens: torch.Tensor = None, causal: bool = False) -> torch.Tensor:
         mask = make_attn_mask(x_lens, self.layers[0].n_heads, causal=causal) if x_lens is not None else None
+        if self.training:
+            for layer in self.layers:
+                x = layer(x, mask)
+            return A.layernorm(x, self.norm) if self.norm is not None else x
         y = run_encoder(self, list(self.layers), x, mask)
         if self.norm is not None:
             y = ops.layernorm(y, self.norm.weight.detach(), self.norm.bias.detach(), eps=self.norm.eps)
