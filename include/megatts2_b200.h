@@ -112,7 +112,10 @@ typedef struct {
   /* operand format of w_tc / the activation planes: MTTS_TC_BF16X3 (three bf16 planes, 6 MMAs per product) or
    * MTTS_TC_F16X2 (two fp16 planes, residual scaled by 2^11, 3 MMAs per product; see mtts_tc_overflow_bind) */
   int32_t tc_fmt;
-  /* leaky slope of post_act on the tensor-core engine is post_slope (as on the FFMA engine) */
+  /* tc_presplit only: the planes in tc_scratch may be a SHARED buffer with a larger halo than this conv needs -
+   * tc_in_tp rows per batch item (0 -> Tout + dil*(k-1)) and this conv's first padded row at tc_in_row0 (HiFi-GAN: the
+   * three ResBlocks of a stage read one split of the up-sampled signal, each at its own row offset) */
+  int32_t tc_in_tp, tc_in_row0;
 } mtts_conv_params;
 
 int mtts_conv1d_f32(const mtts_conv_params* p, void* stream);

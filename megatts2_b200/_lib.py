@@ -35,7 +35,7 @@ class ConvParams(C.Structure):
         ("tc_presplit", i32), ("tc_out_planes", vp), ("tc_out_plane_stride", i64),
         ("tc_out_ld", i32), ("tc_out_tp", i32), ("tc_out_hl", i32), ("tc_out_act", i32), ("tc_out_slope", f32),
         ("tc_partial", vp), ("tc_partial_bytes", i64),
-        ("tc_fmt", i32),
+        ("tc_fmt", i32), ("tc_in_tp", i32), ("tc_in_row0", i32),
     ]
 
 

@@ -44,6 +44,7 @@ struct ConvTcArgs {
   // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
   int32_t splits; float* partial;
   int32_t fmt; int32_t* ovf;   // operand format of the plane output (== the kernel's own NP) and the f16 range flag
+  int32_t row0;                // first padded row of this conv inside a shared plane buffer (0 for its own planes)
   int32_t bo_mode;             // halo form, diagnostics: 1 = put (addr >> 7) & 7 into the descriptors' base-offset field (WRONG on B200)
 };
 
@@ -155,7 +156,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
       const int kb0 = (int)((int64_t)sp * num_k / g.splits), kb1 = (int)((int64_t)(sp + 1) * num_k / g.splits);
       const int nb = tile % num_n, r = tile / num_n;
       const int tb = r % num_t, b = r / num_t;
-      const int trow = tb * BM + (int)crank * 128;               // this CTA's first output row
+      const int trow = tb * BM + (int)crank * 128 + g.row0;      // this CTA's first (padded) input row
       if constexpr (HALO) {
         // the tile's activation rows [trow, trow + 128 + dil * (k - 1)) once, then one weight tile per tap
         const int ab = ait & 1, aph = (ait >> 1) & 1;
@@ -729,7 +730,11 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
   if (p.res && (p.ldr % 4 != 0 || p.res_batch_stride % 4 != 0 || (((uintptr_t)p.res) & 15) != 0)) return false;
   if (p.Tout != p.Tin + 2 * p.pad - p.dil * (p.k - 1)) return false;
   if ((int64_t)p.B * p.Tout < 128) return false;         // tiny problems stay on the exact FFMA engine
-  const int64_t Tp = p.Tout + p.dil * (p.k - 1);
+  int64_t Tp = p.Tout + p.dil * (p.k - 1);
+  if (p.tc_in_tp > 0 || p.tc_in_row0 != 0) {      // shared plane buffer: this conv's rows must lie inside it
+    if (!p.tc_presplit || p.tc_rows_cap > 0 || p.tc_in_row0 < 0 || p.tc_in_tp < p.tc_in_row0 + Tp) return false;
+    Tp = p.tc_in_tp;
+  }
   int64_t rows = (int64_t)p.B * Tp;
   if (p.tc_rows_cap > 0) {
     if (p.k != 1 || p.B != 1 || p.tc_rows_cap < rows) return false;
@@ -746,7 +751,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   int32_t* ovf = tc_ovf_ptr();
   const int halo = p.dil * (p.k - 1);
   const int hl = p.pad, Tp = p.Tout + halo;
-  const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : Tp;     // descriptor rows (>= Tp)
+  const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : (p.tc_in_tp > 0 ? p.tc_in_tp : Tp);     // descriptor rows (>= Tp)
   __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
   const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
   if (!p.tc_presplit) {
@@ -825,7 +830,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
-  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo;
+  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0;
   if (halo_form) {
     if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 0, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 0, 3, 1>(maps, a, st);
     return np == 2 ? conv_tc_launch<64, 128, 0, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 0, 3, 1>(maps, a, st);
@@ -838,6 +843,20 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
     return 0;
   }
   return np == 2 ? conv_tc_dispatch<2>(maps, a, BN, SWB, pair, st) : conv_tc_dispatch<3>(maps, a, BN, SWB, pair, st);
+}
+
+// fp32 (B, T, C) -> padded operand planes (B, hl + T + hr, C) at the 1024-byte-aligned start of `planes_base`
+int split_pad(const float* x, int64_t x_sb, int ldx, int B, int T, int C, int hl, int hr, int pad_mode, int act, float slope,
+              void* planes_base, int fmt, cudaStream_t st) {
+  MTTS_REQUIRE(x && planes_base && C % 4 == 0 && ldx % 4 == 0 && x_sb % 4 == 0 && ((((uintptr_t)x) & 15) == 0), "bad arguments");
+  if (B <= 0 || T <= 0) return 0;
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)planes_base) + 1023) & ~(uintptr_t)1023);
+  const int Tp = T + hl + hr;
+  const int64_t total4 = (int64_t)B * Tp * C / 4;
+  launch_k(split_pad_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, x, x_sb, ldx, T, C, hl, Tp, pad_mode, act, slope, planes,
+           (int64_t)B * Tp * C, total4, fmt, tc_ovf_ptr());
+  MTTS_CHECK_LAUNCH();
+  return 0;
 }
 
 // fp32 (rows, C) -> operand planes (3 | 2, rows, C): the activation split, exposed for packing weights on the device

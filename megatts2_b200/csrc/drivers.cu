@@ -604,7 +604,7 @@ static int64_t hifigan_ws_floats(const mtts_hifigan* h, int B, int T) {
     if (L * C > big) big = L * C;
   }
   const int64_t tcb = h->engine >= 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0;   // + halo rows
-  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + 2 * (tcb / 4 + 64);
+  return (int64_t)B * Tp * h->in_channels + 64 + 5 * ((int64_t)B * big + 64) + 3 * (tcb / 4 + 64);
 }
 
 static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_sb, int mel_ld, int B, int T, float* wav,
@@ -626,9 +626,11 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
   for (int i = 0; i < 5; ++i) bufs[i] = ar.take<float>((int64_t)B * big);
   ConvTc tc{h->engine, nullptr, h->engine >= 1 ? conv_tc_scratch_need(B, 1, big) + 6 * (int64_t)B * 64 * h->ch0 : 0};
   char* planes2 = nullptr;                      // second plane buffer for the fused ResBlock flow
+  char* planes0 = nullptr;                      // the stage input (up-sampled signal), split ONCE for its three ResBlocks
   if (tc.bytes) {
     tc.scratch = ar.take<char>(tc.bytes);
     planes2 = ar.take<char>(tc.bytes);
+    planes0 = ar.take<char>(tc.bytes);
   }
   if (!ar.ok()) return fail(MTTS_ERR_WORKSPACE, "%s: workspace too small (need %lld bytes)", "hifigan", ar.off);
   bool fused = h->engine >= 1 && tc.scratch && planes2;
@@ -667,9 +669,20 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
       attach_tc(p, h->w_up_tc[i], &tc);
       MTTS_TRY(conv1d(p, st));
     }
+    // one split of leaky(oup) with the LARGEST first-conv halo of the stage's ResBlocks; each ResBlock's first conv reads it
+    // at its own row offset (three separate splits of the same signal were 6 % of the vocoder)
+    const bool stage_fused = fused && (Co == 32 || Co == 64 || (Co >= 128 && Co % 32 == 0)) && (int64_t)B * Lo >= 128;
+    int hmax = 0;
+    for (int j = 0; j < h->n_kernels; ++j) {
+      const mtts_hifigan_resblock& rbj = h->resblocks[i * h->n_kernels + j];
+      hmax = rbj.dil[0] * (rbj.k - 1) / 2 > hmax ? rbj.dil[0] * (rbj.k - 1) / 2 : hmax;
+    }
+    const bool shared_split = stage_fused && planes0 && 6 * (int64_t)B * (Lo + 2 * hmax) * Co + 4096 <= tc.bytes;
+    if (shared_split)
+      MTTS_TRY(split_pad(oup, (int64_t)Lo * Co, Co, B, Lo, Co, hmax, hmax, MTTS_PAD_REFLECT, MTTS_ACT_LEAKY, 0.1f, planes0, hfmt, st));
     for (int j = 0; j < h->n_kernels; ++j) {
       const mtts_hifigan_resblock& rb = h->resblocks[i * h->n_kernels + j];
-      const bool fuse_rb = fused && (Co == 32 || Co == 64 || (Co >= 128 && Co % 32 == 0)) && (int64_t)B * Lo >= 128;
+      const bool fuse_rb = stage_fused;
       if (fuse_rb) {
         // Fused plane flow: only the ResBlock input is split by a standalone pass; every conv epilogue writes
         // the NEXT conv's input planes (leaky applied, interior rows), halo_fill materialises the reflect padding.
@@ -680,7 +693,10 @@ static int hifigan_forward(const mtts_hifigan* h, const float* mel, int64_t mel_
           mtts_conv_params c1 = conv_same_params(xcur, rb.w1[m], rb.b1[m], nullptr, B, Lo, Co, Co, rb.k, rb.dil[m], MTTS_PAD_REFLECT);
           c1.pre_act = MTTS_ACT_LEAKY; c1.pre_slope = 0.1f;
           c1.w_tc = rb.w1_tc[m]; c1.tc_scratch = tc.scratch; c1.tc_scratch_bytes = tc.bytes; c1.tc_fmt = hfmt;
-          c1.tc_presplit = (m > 0);              // m == 0: split_pad(leaky(oup)) runs inside conv_tc
+          c1.tc_presplit = (m > 0);              // m == 0 without the shared split: split_pad(leaky(oup)) runs inside conv_tc
+          if (m == 0 && shared_split) {
+            c1.tc_presplit = 1; c1.tc_scratch = planes0; c1.tc_in_tp = Lo + 2 * hmax; c1.tc_in_row0 = hmax - h1;
+          }
           c1.y = nullptr;
           c1.tc_out_planes = reinterpret_cast<void*>((((uintptr_t)planes2) + 1023) & ~(uintptr_t)1023);
           c1.tc_out_tp = Lo + 2 * h2; c1.tc_out_hl = h2; c1.tc_out_ld = Co;

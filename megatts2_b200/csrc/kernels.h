@@ -88,6 +88,8 @@ int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, i
               const float* res, int ldr, float* y, int ldy, int pre_act, float pre_slope, int post_act,
               float out_scale, void* scratch, int64_t scratch_bytes, int64_t rows_cap, int fmt, cudaStream_t st);
 int split_planes(const float* x, int ldx, int64_t rows, int C, void* planes, int fmt, cudaStream_t st);
+int split_pad(const float* x, int64_t x_sb, int ldx, int B, int T, int C, int hl, int hr, int pad_mode, int act, float slope,
+              void* planes_base, int fmt, cudaStream_t st);
 int tc_overflow_bind(int32_t* flag);
 int mask_tail(float* x, int B, int rows, int L, const int32_t* keep, cudaStream_t st);
 int layernorm(const float* x, int ldx, const float* gamma, const float* beta, const float* res, int ldr, float* y,

@@ -201,14 +201,17 @@ layernorm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamm
 }
 int layernorm_bwd(const float* x, const float* gamma, const float* dy, float* dx, float* partial, int64_t rows, int C, float eps,
                   cudaStream_t st) {
-  MTTS_REQUIRE(x && gamma && dy && dx && partial && C > 0 && C <= 4096, "bad arguments");
+  MTTS_REQUIRE(x && gamma && dy && dx && partial && C > 0 && C <= 3072, "bad arguments (C <= 3072: 8 rows x 2 x C floats of shared memory)");
   if (rows <= 0) return 0;
   const size_t smem = sizeof(float) * 16 * (size_t)C;
   static std::atomic<uint64_t> configured{0};
   const int dev = cur_device();
   if (smem > 48 * 1024 && !(configured.load(std::memory_order_relaxed) & (1ull << dev))) {
-    cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 4096 * 4);
-    if (e != cudaSuccess) return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "layernorm_bwd", (long long)e);
+    cudaError_t e = cudaFuncSetAttribute(layernorm_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 16 * 3072 * 4);
+    if (e != cudaSuccess) {
+      cudaGetLastError();      // do not leave the error for the next launch check
+      return fail(MTTS_ERR_CUDA, "%s: cudaFuncSetAttribute failed: %lld", "layernorm_bwd", (long long)e);
+    }
     configured.fetch_or(1ull << dev, std::memory_order_relaxed);
   }
   launch_k(layernorm_bwd_kernel, (unsigned)cdiv64(rows, 8), 256, smem, st, x, gamma, dy, dx, partial, rows, C, eps);

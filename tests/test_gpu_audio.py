@@ -29,7 +29,7 @@ def test_resample_vs_oracle(orig):
         ref = ref_audio.resample(x[b, :lens[b]].numpy(), orig, 16000)
         n = int(lo[b])
         assert n == len(ref)
-        assert np.abs(y[b, :n].cpu().numpy() - ref).max() < 2e-5          # fp32 FIR of <= 815 taps vs the fp64 oracle
+        assert np.abs(y[b, :n].cpu().numpy() - ref).max() < 5e-5          # fp32 FIR of <= 815 taps (fp32 table) vs the fp64 oracle
         assert float(y[b, n:].abs().max()) == 0.0 if n < y.shape[1] else True
     # the un-ragged call equals torchaudio itself (same fp32 table, fp32 accumulation)
     import torchaudio

@@ -43,13 +43,17 @@ def _compare(model, ref_grads, loss, ref_loss, tol):
     assert abs(loss - ref_loss) <= 2e-4 * max(1.0, abs(ref_loss)), (loss, ref_loss)
     worst = 0.0
     n = 0
+    # gradients that are zero in exact arithmetic (the key bias of an attention layer: softmax is invariant to a constant
+    # shift of every score of a row) are pure rounding noise on both sides: errors are taken relative to at least 1e-5 of
+    # the largest gradient in the model
+    floor = 1e-5 * max(float(r.abs().max()) for r in ref_grads.values())
     for name, p in model.named_parameters():
         if name not in ref_grads:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
             continue
         assert p.grad is not None, f"no gradient reached {name}"
         g, r = p.grad.detach().cpu(), ref_grads[name]
-        err = (g - r).abs().max().item() / max(r.abs().max().item(), 1e-12)
+        err = (g - r).abs().max().item() / max(r.abs().max().item(), floor)
         worst = max(worst, err)
         assert err < tol, f"{name}: relative gradient error {err:.3e}"
         n += 1
