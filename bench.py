@@ -180,11 +180,11 @@ def make_inputs(indices, pin=True):
     return wav, phone, forced
 
 
-def gpu_step(tts, wav_d, phone_d, forced_d, revocode=True, intermediates=False):
+def gpu_step(tts, wav_d, phone_d, forced_d, revocode=True, intermediates=False, overlap=None):
     from megatts2_b200.modules.tokenizer import extract_mel_spec
     mel = extract_mel_spec(wav_d, frames_major=True)                  # (B, 500, 80)
     return tts.synthesize(phone_d, mel, forced_durations=forced_d, prompt_mels=mel if revocode else None,
-                          return_intermediates=intermediates)
+                          return_intermediates=intermediates, overlap_prompt=overlap)
 
 
 # ------------------------------------------------------------------------------------------ CPU workers (oracle port)
@@ -339,8 +339,10 @@ def run_b200(args):
     result = None
     if rank == 0:
         # ---- roofline leg: per-launch CUDA events around every tap-GEMM launch of ONE step
+        # (single stream for this leg: with the prompt re-vocode overlapped on its side stream the per-launch times of two
+        #  concurrently running kernels would be summed)
         lib.mtts_profile_begin()
-        gpu_step(tts, wav_d, phone_d, forced_d, revocode)
+        gpu_step(tts, wav_d, phone_d, forced_d, revocode, overlap=False)
         gms, gfl, gn = C.c_double(), C.c_double(), C.c_int64()
         L.check(lib.mtts_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn)))
         log(f"roofline leg: {gn.value} tap-GEMM launches, {gms.value:.1f} ms, {gfl.value / 1e12:.2f} TFLOP")

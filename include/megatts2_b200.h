@@ -60,6 +60,10 @@ int mtts_trace_end(char* buf, int32_t buf_len);
  * and reruns the batch on BF16X3. */
 enum { MTTS_TC_BF16X3 = 0, MTTS_TC_F16X2 = 1 };
 int mtts_tc_overflow_bind(int32_t* flag_dev);
+/* SM budget of the calling host thread's subsequent launches (0 = the whole device): the persistent tensor-core kernels
+ * size their grids from it, so work enqueued on two streams can share the device (the prompt re-vocode of Megatts.forward
+ * runs beside the latency-bound AR loops). */
+int mtts_set_sm_limit(int32_t n_sms);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };

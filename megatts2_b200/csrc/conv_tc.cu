@@ -564,6 +564,14 @@ int cur_device() {
   cudaGetDevice(&dev);
   return dev < 0 || dev >= MAX_DEV ? 0 : dev;
 }
+// SM budget of the calling host thread's launches (0 = the whole device).  The persistent tensor-core kernels size their
+// grids from it, so two streams can share the device: the vocoder pass that re-vocodes the prompt runs on a side stream
+// with a reduced budget while the latency-bound AR loops use the SMs it leaves free (models/megatts2.py).
+static thread_local int g_sm_limit = 0;
+int set_sm_limit(int n) {
+  g_sm_limit = n > 0 ? n : 0;
+  return 0;
+}
 int cur_device_sms() {
   const int dev = cur_device();
   if (!g_dev[dev].sms) {
@@ -571,7 +579,8 @@ int cur_device_sms() {
     cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
     g_dev[dev].sms = n > 0 ? n : 1;
   }
-  return g_dev[dev].sms;
+  const int all = g_dev[dev].sms;
+  return g_sm_limit > 0 && g_sm_limit < all ? g_sm_limit : all;
 }
 int32_t* tc_ovf_ptr() { return g_dev[cur_device()].ovf; }
 int tc_overflow_bind(int32_t* flag) {

@@ -494,7 +494,7 @@ class Megatts(nn.Module):
     @torch.no_grad()
     def synthesize(self, phone_tokens: torch.Tensor, mels: torch.Tensor, forced_durations: torch.Tensor = None,
                    return_intermediates: bool = False, causal_decode: bool = False, prompt_mels: torch.Tensor = None,
-                   return_lengths: bool = False, check_range: bool = True):
+                   return_lengths: bool = False, check_range: bool = True, overlap_prompt: bool = None):
         """phone_tokens (B,Tp) int64, mels (B,Tm,80) prompt mel (frames-major) -> wav (B,1,256*(max sum d + 10)).
         Steps = models/megatts2.py:354-373; every utterance's result equals the reference's batch-1 run on it
         (utterances are independent; the only cross-utterance coupling would be the zero rows the LengthRegulator
@@ -508,21 +508,46 @@ class Megatts(nn.Module):
         ``return_lengths``: also return the valid sample count per utterance (prompt part included).
         ``causal_decode=True`` swaps both AR loops for the opt-in causal KV-cache decode (training semantics; NOT the
         reference's infer() - different ids).
+        ``overlap_prompt``: run the prompt re-vocode on a side stream with a reduced SM budget beside the AR loops (default:
+        on, MEGATTS2_REVOCODE_SMS SMs; False = after the synthesis on the calling stream).
         ``check_range``: with the f16x2 operand engine, read the range flag after the batch (one 4-byte readback) and,
         if any activation left the fp16 range, redo the batch on the bf16x3 engine."""
         dev = phone_tokens.device
-        out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels)
+        out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels, overlap_prompt)
         if check_range and pack.default_engine() == pack.ENGINE_F16X2 and ops.tc_overflow(dev):
             import warnings
             warnings.warn("megatts2_b200: an activation left the fp16 range of the f16x2 operand split; "
                           "re-running this batch on the bf16x3 engine")
             with pack.engine_scope(pack.ENGINE_BF16X3):
-                out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels)
+                out = self._synthesize(phone_tokens, mels, forced_durations, causal_decode, prompt_mels, overlap_prompt)
         if return_intermediates:
             return out
         return (out["wav"], out["wav_lens"]) if return_lengths else out["wav"]
 
-    def _synthesize(self, phone_tokens, mels, forced_durations, causal_decode, prompt_mels):
+    def _revocode_sms(self):
+        """SM budget of the prompt re-vocode when it runs beside the AR loops (MEGATTS2_REVOCODE_SMS; 0 = run it after the
+        synthesis on the main stream, no overlap)."""
+        import os
+        return int(os.environ.get("MEGATTS2_REVOCODE_SMS", "64"))
+
+    def _synthesize(self, phone_tokens, mels, forced_durations, causal_decode, prompt_mels, overlap_prompt=None):
+        # The prompt re-vocode (:371-372) depends on nothing the synthesis computes: it is enqueued FIRST, on a side stream
+        # with a reduced SM budget, and overlaps the ADM / PLM loops whose small launches leave most SMs idle.
+        pw, side = None, None
+        if prompt_mels is not None and self._revocode_sms() > 0 and overlap_prompt is not False:
+            self.hifi_gan.generator._plan_get()          # weights are packed on the calling stream, before the fork
+            main = torch.cuda.current_stream(prompt_mels.device)
+            if getattr(self, "_side_stream", None) is None:
+                self._side_stream = torch.cuda.Stream(device=prompt_mels.device)
+            side = self._side_stream
+            side.wait_stream(main)
+            prompt_mels.record_stream(side)
+            with torch.cuda.stream(side):
+                L.lib().mtts_set_sm_limit(self._revocode_sms())
+                try:
+                    pw = self.hifi_gan.decode_batch_cl(prompt_mels)
+                finally:
+                    L.lib().mtts_set_sm_limit(0)
         tc_latent = self.generator.mrte.tc_latent(phone_tokens, mels)
         adm_decode = self.adm.infer_causal if causal_decode else self.adm.infer
         plm_decode = self.plm.infer_causal if causal_decode else self.plm.infer
@@ -551,7 +576,11 @@ class Megatts(nn.Module):
                 wav[idx, :, :wg.shape[-1]] = wg
         wav_lens = [hop * (t + 2 * pad) for t in totals]
         if prompt_mels is not None:
-            pw = self.hifi_gan.decode_batch_cl(prompt_mels)           # (B, 1, hop*(Tq + 2 pad))   (:371-372)
+            if pw is None:
+                pw = self.hifi_gan.decode_batch_cl(prompt_mels)       # (B, 1, hop*(Tq + 2 pad))   (:371-372)
+            else:
+                torch.cuda.current_stream(pw.device).wait_stream(side)
+                pw.record_stream(torch.cuda.current_stream(pw.device))
             wav = torch.cat([pw, wav], dim=-1)                        # (:373)
             wav_lens = [n + pw.shape[-1] for n in wav_lens]
         return dict(tc_latent=tc_latent, dt=dt, tc_latent_expand=tc_expand, tc8=tc8, p_codes=p_codes,

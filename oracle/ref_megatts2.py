@@ -74,11 +74,11 @@ def mel_spectrogram(wav, n_fft=1024, hop=256, n_mels=80, f_min=0.0, f_max=8000.0
     SURVEY.md Appendix B."""
     lead = wav.shape[:-1]
     x = wav.reshape(-1, wav.shape[-1]).to(torch.float32)
-    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float32)   # torchaudio's window_fn default
+    win = torch.hann_window(n_fft, periodic=True, dtype=torch.float32, device=x.device)   # torchaudio's window_fn default
     spec = torch.stft(x, n_fft=n_fft, hop_length=hop, win_length=n_fft, window=win, center=True,
                       pad_mode="reflect", normalized=False, onesided=True, return_complex=True)
     mag = spec.abs()                                        # (N, 513, F)   power = 1
-    fb = slaney_fbanks(n_fft // 2 + 1, f_min, f_max, n_mels, sr)
+    fb = slaney_fbanks(n_fft // 2 + 1, f_min, f_max, n_mels, sr).to(x.device)
     mel = torch.matmul(mag.transpose(-1, -2), fb).transpose(-1, -2)
     out = torch.log(torch.clamp(mel, min=clamp))
     return out.reshape(*lead, n_mels, out.shape[-1])

@@ -31,7 +31,7 @@ def main():
     rt = torch.cuda.cudart()
     if a.stage == "all":
         rt.cudaProfilerStart()
-        bench.gpu_step(tts, wav, phone, forced)
+        bench.gpu_step(tts, wav, phone, forced, overlap=False)
         torch.cuda.synchronize()
         rt.cudaProfilerStop()
         return
