@@ -74,7 +74,8 @@ static inline int64_t align_up(int64_t a, int64_t b) { return cdiv64(a, b) * b; 
 struct Arena {
   char* base;
   int64_t size, off;
-  Arena(void* p, int64_t n) : base((char*)p), size(n), off(0) {}
+  // the base is rounded up to 256 bytes, so a raw C caller's workspace need not be aligned (float4 / TMA carving is)
+  Arena(void* p, int64_t n) : base((char*)((((uintptr_t)p) + 255) & ~(uintptr_t)255)), size(n - (int64_t)(base - (char*)p)), off(0) {}
   template <typename T>
   T* take(int64_t n) {
     off = align_up(off, 256);

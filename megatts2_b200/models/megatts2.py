@@ -508,8 +508,8 @@ class Megatts(nn.Module):
         ``return_lengths``: also return the valid sample count per utterance (prompt part included).
         ``causal_decode=True`` swaps both AR loops for the opt-in causal KV-cache decode (training semantics; NOT the
         reference's infer() - different ids).
-        ``overlap_prompt``: run the prompt re-vocode on a side stream with a reduced SM budget beside the AR loops (default:
-        on, MEGATTS2_REVOCODE_SMS SMs; False = after the synthesis on the calling stream).
+        ``overlap_prompt``: experimental - with MEGATTS2_REVOCODE_SMS = n > 0 the prompt re-vocode runs on a side stream with
+        an n-SM budget beside the AR loops (measured slower on B200, so off by default); False forces the sequential form.
         ``check_range``: with the f16x2 operand engine, read the range flag after the batch (one 4-byte readback) and,
         if any activation left the fp16 range, redo the batch on the bf16x3 engine."""
         dev = phone_tokens.device
@@ -525,10 +525,12 @@ class Megatts(nn.Module):
         return (out["wav"], out["wav_lens"]) if return_lengths else out["wav"]
 
     def _revocode_sms(self):
-        """SM budget of the prompt re-vocode when it runs beside the AR loops (MEGATTS2_REVOCODE_SMS; 0 = run it after the
-        synthesis on the main stream, no overlap)."""
+        """SM budget of the prompt re-vocode when it runs beside the AR loops on a side stream (MEGATTS2_REVOCODE_SMS; 0 = run
+        it after the synthesis on the calling stream).  Default 0: measured on B200 (profiles/r2j_revocode_overlap_sweep.log)
+        every budget made the step SLOWER (421 ms sequential vs 447 ms at 96 SMs ... 660 ms at 64): the vocoder's persistent
+        CTAs hold their SMs for ~1 ms at a time and the AR loops' ~11 k short dependent launches queue behind them."""
         import os
-        return int(os.environ.get("MEGATTS2_REVOCODE_SMS", "64"))
+        return int(os.environ.get("MEGATTS2_REVOCODE_SMS", "0"))
 
     def _synthesize(self, phone_tokens, mels, forced_durations, causal_decode, prompt_mels, overlap_prompt=None):
         # The prompt re-vocode (:371-372) depends on nothing the synthesis computes: it is enqueued FIRST, on a side stream
