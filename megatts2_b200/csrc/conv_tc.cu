@@ -63,13 +63,18 @@ struct ConvTcCfg {
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by one CTA
   static constexpr int B_PLANE = B_ROWS * SWB;
   static constexpr int STAGE = HALO ? NP * B_PLANE : NP * (A_PLANE + B_PLANE);
-  static constexpr int A_REGION = HALO ? 2 * NP * A_PLANE : 0;   // two halo-tile buffers
+  // halo-tile buffers: a tile's rows are requested when the buffer of the tile A_BUFS back is released, i.e. A_BUFS - 1 tiles
+  // of MMA time ahead; the k = 3 convolutions have ~1 us of MMA work per tile against ~1.3 us of HBM latency, so two
+  // buffers left the tensor pipe waiting on every tile
+  static constexpr int A_BUFS = HALO ? (SWB == 64 ? 4 : (NP == 2 ? 3 : 2)) : 0;
+  static constexpr int A_REGION = A_BUFS * NP * A_PLANE;
   static constexpr int EPI_STAGE = 8 * 32 * 20 * 4;          // epilogue transpose buffers: 8 warps x [32 rows][20 floats]
   static constexpr int STAGES_RAW = (227 * 1024 - 1024 - 256 - EPI_STAGE - A_REGION) / STAGE;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : (STAGES_RAW < 2 ? 2 : STAGES_RAW);
   static constexpr int SMEM = A_REGION + STAGES * STAGE + 1024 + 256 + EPI_STAGE;
   static constexpr int NACC = (4 * BN > 512) ? 1 : 2;            // accumulator buffers: BN = 256 fills TMEM with one
   static constexpr int TMEM_COLS = NACC * 2 * BN < 32 ? 32 : NACC * 2 * BN;   // NACC x (main + correction) x BN
+  static_assert(SMEM <= 227 * 1024 && STAGES_RAW >= 2, "shared-memory budget");
 };
 
 template <int BN, int SWB, int PAIR, int NP, int HALO>
@@ -90,7 +95,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
   const uint32_t full_bar = bars, empty_bar = bars + 8 * STAGES;
   const uint32_t tfull_bar = bars + 16 * STAGES, tempty_bar = tfull_bar + 16;
   const uint32_t tmem_slot = tempty_bar + 16;
-  const uint32_t afull_bar = tmem_slot + 16, aempty_bar = afull_bar + 16;   // HALO only (8 * STAGES * 2 + 80 <= 256)
+  const uint32_t afull_bar = tmem_slot + 16, aempty_bar = afull_bar + 32;   // HALO only (16 * STAGES + 48 + 64 <= 256)
   uint32_t* tmem_slot_ptr = reinterpret_cast<uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
   float* epi_stage = reinterpret_cast<float*>(smem_raw + (bars + 256 - smem_u32(smem_raw)));   // 16-byte aligned
 
@@ -116,7 +121,9 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
     for (int s = 0; s < 2; ++s) {
       mbar_init(tfull_bar + 8 * s, 1);
       mbar_init(tempty_bar + 8 * s, PAIR ? 16 : 8);     // one arrive per epilogue warp (8 warps per CTA)
-      if constexpr (HALO) {
+    }
+    if constexpr (HALO) {
+      for (int s = 0; s < Cfg::A_BUFS; ++s) {
         mbar_init(afull_bar + 8 * s, 1);
         mbar_init(aempty_bar + 8 * s, 1);
       }
@@ -159,7 +166,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
       const int trow = tb * BM + (int)crank * 128 + g.row0;      // this CTA's first (padded) input row
       if constexpr (HALO) {
         // the tile's activation rows [trow, trow + 128 + dil * (k - 1)) once, then one weight tile per tap
-        const int ab = ait & 1, aph = (ait >> 1) & 1;
+        const int ab = ait % Cfg::A_BUFS, aph = (ait / Cfg::A_BUFS) & 1;
         ++ait;
         mbar_wait(aempty_bar + 8 * ab, aph ^ 1);
         if (leader) {
@@ -227,7 +234,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         const uint32_t d_main = tmem_base + as * (2 * BN);
         const uint32_t d_corr = d_main + BN;
         if constexpr (HALO) {
-          const int ab = it & 1, aph = (it >> 1) & 1;
+          const int ab = it % Cfg::A_BUFS, aph = (it / Cfg::A_BUFS) & 1;
           mbar_wait(afull_bar + 8 * ab, aph);
           for (int kb = kb0; kb < kb1; ++kb) {          // kb == tap (one K-slab per tap)
             mbar_wait(full_bar + 8 * stage, phase);
@@ -327,35 +334,61 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
     const int ew = warp - 4;                      // 0..7
     const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
     const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
+    // The bias / residual rows of a unit are REQUESTED ONE UNIT AHEAD (across tile boundaries too): a residual row comes
+    // from HBM (~1 us), and requested at the top of its own unit that latency was exposed once per unit - the epilogue of
+    // the residual-carrying layers (HiFi-GAN convs2, out-projection, FF2) took ~2.5x the MMA time of their tiles.
+    struct UnitLd { float4 bv, rv[4]; };
+    const int chunk = lane & 3, rsub = lane >> 2;
+    auto unit_ld = [&](int item_, int u_, UnitLd& L) {
+      const int tile_ = item_ / g.splits;
+      const int nb_ = tile_ % num_n, r0_ = tile_ / num_n;
+      const int tb_ = r0_ % num_t, b_ = r0_ / num_t;
+      const int n_ = nb_ * BN + u_ * 16 + chunk * 4;
+      const int tbase_ = tb_ * BM + (int)crank * 128 + q * 32;
+      const bool on = n_ < g.Cout && g.splits == 1;
+      L.bv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (on && g.bias) L.bv = __ldg(reinterpret_cast<const float4*>(g.bias + n_));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int tt = tbase_ + i * 8 + rsub;
+        L.rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (on && g.res && tt < g.T && !g.out_shift)
+          L.rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b_ * g.res_sb + (int64_t)tt * g.ldr + n_);
+      }
+    };
+    UnitLd cur, nxt;
+    if (worker < num_tiles) unit_ld(worker, half, cur);
     int it = 0;
     for (int item = worker; item < num_tiles; item += nworkers, ++it) {
       const int sp = item % g.splits, tile = item / g.splits;
       const int nb = tile % num_n, r0 = tile / num_n;
       const int tb = r0 % num_t, b = r0 / num_t;
       const int as = it % NACC, aphase = (it / NACC) & 1;
-      bool waited = false;      // the accumulator wait is deferred until the first unit's global loads are in flight
+      bool waited = false;      // the accumulator wait is deferred until the next unit's global loads are in flight
       // Each unit = this warp's 32 rows x 16 columns.  The accumulators arrive row-per-lane (TMEM lane == row);
       // writing them out like that would make every global instruction touch 32 different lines, so the unit
       // is transposed through a padded shared buffer and ALL global traffic of the epilogue (y, residual,
-      // accumulate, bf16 planes) is issued as 8 rows x 64 contiguous bytes per instruction.
+      // accumulate, operand planes) is issued as 8 rows x 64 contiguous bytes per instruction.
       float* stg = epi_stage + ew * (32 * 20);
-      const int chunk = lane & 3, rsub = lane >> 2;
       const int t_base = tb * BM + (int)crank * 128 + q * 32;
 #pragma unroll 1
       for (int u = half; u < BN / 16; u += 2) {
         const int n = nb * BN + u * 16 + chunk * 4;
         const bool ncol = n < g.Cout;                 // Cout % 4 == 0: a 4-wide chunk is all-in or all-out
-        // independent global loads first (bias once per lane; residual / accumulate per owned row)
-        float4 bvec = make_float4(0.f, 0.f, 0.f, 0.f), rv[4], ov[4];
-        if (ncol && g.bias && g.splits == 1) bvec = __ldg(reinterpret_cast<const float4*>(g.bias + n));
+        {   // request the NEXT unit's rows (same tile, or the first unit of this warp's next tile)
+          int nitem = item, nu = u + 2;
+          if (nu >= BN / 16) { nitem = item + nworkers; nu = half; }
+          if (nitem < num_tiles) unit_ld(nitem, nu, nxt);
+        }
+        const float4 bvec = cur.bv;
+        float4 rv[4], ov[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const int tt = t_base + i * 8 + rsub;
-          rv[i] = ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ncol && tt < g.T && !g.out_shift && g.splits == 1) {
-            if (g.res) rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n);
-            if (g.accumulate) ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
-          }
+          rv[i] = cur.rv[i];
+          ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (ncol && tt < g.T && !g.out_shift && g.splits == 1 && g.accumulate)
+            ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
         }
         if (!waited) {
           mbar_wait(tfull_bar + 8 * as, aphase);
@@ -407,6 +440,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
           }
         }
         __syncwarp();   // the staging buffer is reused by the next unit
+        cur = nxt;
       }
       if (!waited) {
         mbar_wait(tfull_bar + 8 * as, aphase);

@@ -2,7 +2,7 @@
 # GPU call K: PLM-stage ncu captures (pair GEMM / attention / LayerNorm), reference arm, full suite
 set -u
 mkdir -p gpurun_out
-timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:conv_tc_kernel --launch-skip 3300 -c 6 -f \
+timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:conv_tc_kernel --launch-skip 2700 -c 8 -f \
   -o gpurun_out/r2k_plm_gemm python tools/profile_step.py --batch 64 --stage plm > gpurun_out/r2k_ncu_1.log 2>&1; tail -1 gpurun_out/r2k_ncu_1.log
 timeout 600 ncu --set full --clock-control none --profile-from-start off -k regex:attn_kernel --launch-skip 650 -c 3 -f \
   -o gpurun_out/r2k_plm_attn python tools/profile_step.py --batch 64 --stage plm > gpurun_out/r2k_ncu_2.log 2>&1; tail -1 gpurun_out/r2k_ncu_2.log
