@@ -44,6 +44,7 @@ struct ConvTcArgs {
   // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
   int32_t splits; float* partial;
   int32_t fmt; int32_t* ovf;   // operand format of the plane output (== the kernel's own NP) and the f16 range flag
+  int32_t epi_prefetch;        // epilogue requests bias / residual rows one unit ahead (MEGATTS2_TC_EPI_PREFETCH=1; default off, measured neutral)
   int32_t row0;                // first padded row of this conv inside a shared plane buffer (0 for its own planes)
   int32_t bo_mode;             // halo form, diagnostics: 1 = put (addr >> 7) & 7 into the descriptors' base-offset field (WRONG on B200)
 };
@@ -375,10 +376,12 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
       for (int u = half; u < BN / 16; u += 2) {
         const int n = nb * BN + u * 16 + chunk * 4;
         const bool ncol = n < g.Cout;                 // Cout % 4 == 0: a 4-wide chunk is all-in or all-out
-        {   // request the NEXT unit's rows (same tile, or the first unit of this warp's next tile)
+        if (g.epi_prefetch) {   // request the NEXT unit's rows (same tile, or the first unit of this warp's next tile)
           int nitem = item, nu = u + 2;
           if (nu >= BN / 16) { nitem = item + nworkers; nu = half; }
           if (nitem < num_tiles) unit_ld(nitem, nu, nxt);
+        } else {
+          unit_ld(item, u, cur);
         }
         const float4 bvec = cur.bv;
         float4 rv[4], ov[4];
@@ -440,7 +443,7 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
           }
         }
         __syncwarp();   // the staging buffer is reused by the next unit
-        cur = nxt;
+        if (g.epi_prefetch) cur = nxt;
       }
       if (!waited) {
         mbar_wait(tfull_bar + 8 * as, aphase);
@@ -625,7 +628,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int epi_prefetch; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -643,6 +646,8 @@ static const CtcEnv& ctc_env() {
     const char* be = getenv("MEGATTS2_TC_HALO_BO");       // 1: base-offset field set in the row-shifted descriptors (diagnostics)
     e.halo = !(he && he[0] == '0');
     e.halo_bo = be ? atoi(be) : 0;
+    const char* ee = getenv("MEGATTS2_TC_EPI_PREFETCH");
+    e.epi_prefetch = ee ? atoi(ee) : 0;   // measured: no gain (profiles/r2m_epi_prefetch_ab.log)
     return e;
   }();
   return env;
@@ -873,7 +878,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
-  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0;
+  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0; a.epi_prefetch = env.epi_prefetch;
   if (halo_form) {
     if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 0, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 0, 3, 1>(maps, a, st);
     return np == 2 ? conv_tc_launch<64, 128, 0, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 0, 3, 1>(maps, a, st);
