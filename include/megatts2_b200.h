@@ -178,8 +178,14 @@ int mtts_vq_gather_f32(const int64_t* idx, int32_t idx_ld, const float* embed, i
 /* extract_mel_spec (modules/tokenizer.py:107-125): reflect-padded
  * 1024-point STFT (hop 256, window table given), magnitude, banded mel filterbank,
  * log(max(., clamp)).  wav (B, L) -> out[b*out_sb + m*out_sm + f*out_sf], f < 1 + L/256.
- * The filterbank is passed in banded form: for mel m, taps fb_w[fb_off[m] .. fb_off[m+1])
- * apply to bins fb_start[m] ...   n_fft must be 1024, hop 256. */
+ * The filterbank is passed in GROUPED banded form (the host packs it once, like a weight plane;
+ * megatts2_b200/modules/tokenizer.py:pack_grouped_filterbank).  Mels are taken in groups of 4, G = ceil(n_mels / 4):
+ *   fb_start[4 G]  first bin read for each mel, a multiple of 4 (slots past n_mels: 0)
+ *   fb_off[G + 1]  float offset of each group's block in fb_w; a block holds 4 * len_g floats, len_g a multiple of 4
+ *                  covering the longest (aligned) band of the group
+ *   fb_w           16-byte aligned; block g, element i * len_g + t = weight of mel 4 g + i at bin fb_start[4 g + i] + t
+ *                  (0 outside its band); fb_start[m] + len_g <= 516 for every mel (bins 513..515 read as zero).
+ * n_fft must be 1024, hop 256, n_mels <= 128. */
 int mtts_mel_spectrogram_f32(const float* wav, int64_t wav_sb, int32_t B, int32_t L,
                              const float* window, const float* fb_w, const int32_t* fb_off,
                              const int32_t* fb_start, int32_t n_mels, float clamp_min,
@@ -263,6 +269,35 @@ int mtts_colsum_f32(const float* in, int64_t ld, int64_t rows, int32_t C, float*
 int mtts_relu_bwd_f32(const float* y, const float* dy, float* dx, int64_t n, void* stream);
 int mtts_embedding_bwd_f32(const int64_t* ids, const float* dy, int64_t rows, int32_t D, int32_t vocab, float* dW, void* stream);
 int mtts_rowdot_f32(const float* a, const float* b, int64_t rows, int32_t C, int32_t period, float* out, void* stream);
+
+/* Training-only pieces of the VQ codebook: EuclideanCodebook.forward in train mode and the
+ * straight-through / commitment step of VectorQuantization.forward.
+ * mtts_kmeans_assign_f32: idx[n] = first argmin_k sum_d (x[n,d] - means[k,d])^2 - the bucket step of kmeans()
+ *   (modules/quantization/core_vq.py:81-86; direct differences, not the expanded form of quantize).  D <= 512.
+ * mtts_vq_cluster_sum_f32: sum[k,:] = sum_{n: idx[n]=k} x[n,:] accumulated in sample order, cnt[k] = bucket size as
+ *   float - bincount + scatter_add_ of kmeans (:87-92) and embed_onehot.sum(0) / x.t() @ embed_onehot of the EMA step
+ *   (:220-222).
+ * mtts_kmeans_update_f32: means[k] = cnt[k] > 0 ? sum[k] / cnt[k] : means[k]   (:88-95).
+ * mtts_vq_ema_update_f32: cluster_size <- decay cs + (1-decay) cnt; embed_avg <- decay ea + (1-decay) sum;
+ *   embed = embed_avg / ((cs + eps) / (sum(cs) + K eps) * sum(cs))   (ema_inplace, laplace_smoothing; :217-229).
+ *   scratch: K floats.
+ * mtts_vq_replace_rows_f32: embed[k] = samples[pick[k]] where cluster_size[k] < thr   (expire_codes_ / replace_, :151-169;
+ *   the caller draws pick = sample_vectors' indices).
+ * mtts_vq_ste_commit_f32: out = x + (q - x) (the straight-through value as the reference rounds it) and
+ *   loss[0] = mean((out - x)^2) (F.mse_loss(quantize.detach(), x), :303-311); partials: 256 floats of scratch.
+ * mtts_vq_ste_commit_bwd_f32: dx = g_out + g_loss[0] * scale * (x - out), scale = commitment_weight * 2 / numel;
+ *   g_out or g_loss may be NULL. */
+int mtts_kmeans_assign_f32(const float* x, const float* means, int32_t N, int32_t K, int32_t D, int64_t* idx, void* stream);
+int mtts_vq_cluster_sum_f32(const float* x, const int64_t* idx, int32_t N, int32_t K, int32_t D, float* sum, float* cnt,
+                            void* stream);
+int mtts_kmeans_update_f32(float* means, const float* sum, const float* cnt, int32_t K, int32_t D, void* stream);
+int mtts_vq_ema_update_f32(float* cluster_size, float* embed_avg, float* embed, const float* sum, const float* cnt,
+                           int32_t K, int32_t D, float decay, float eps, float* scratch, void* stream);
+int mtts_vq_replace_rows_f32(float* embed, const float* samples, const int64_t* pick, const float* cluster_size, float thr,
+                             int32_t K, int32_t D, int32_t N, void* stream);
+int mtts_vq_ste_commit_f32(const float* x, const float* q, int64_t n, float* out, float* partials, float* loss, void* stream);
+int mtts_vq_ste_commit_bwd_f32(const float* x, const float* out, const float* g_out, const float* g_loss, float scale,
+                               int64_t n, float* dx, void* stream);
 
 /* x (B, rows, L) contiguous: x[b, r, keep[b]:] = 0 in place - speechbrain HIFIGAN.mask_noise behind
  * decode_batch(mel, mel_lens, hop_len) (reference call site models/megatts2.py:370). */

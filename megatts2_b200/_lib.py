@@ -132,6 +132,13 @@ SIGNATURES = {
     "mtts_relu_bwd_f32": (C.c_int, [vp, vp, vp, i64, vp]),
     "mtts_embedding_bwd_f32": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
     "mtts_rowdot_f32": (C.c_int, [vp, vp, i64, i32, i32, vp, vp]),
+    "mtts_kmeans_assign_f32": (C.c_int, [vp, vp, i32, i32, i32, vp, vp]),
+    "mtts_vq_cluster_sum_f32": (C.c_int, [vp, vp, i32, i32, i32, vp, vp, vp]),
+    "mtts_kmeans_update_f32": (C.c_int, [vp, vp, vp, i32, i32, vp]),
+    "mtts_vq_ema_update_f32": (C.c_int, [vp, vp, vp, vp, vp, i32, i32, f32, f32, vp, vp]),
+    "mtts_vq_replace_rows_f32": (C.c_int, [vp, vp, vp, vp, f32, i32, i32, i32, vp]),
+    "mtts_vq_ste_commit_f32": (C.c_int, [vp, vp, i64, vp, vp, vp, vp]),
+    "mtts_vq_ste_commit_bwd_f32": (C.c_int, [vp, vp, vp, vp, f32, i64, vp, vp]),
     "mtts_layernorm_f32": (C.c_int, [vp, i32, vp, vp, vp, i32, vp, i32, i64, i32, f32, i32, i32, vp]),
     "mtts_attention_f32": (C.c_int, [C.POINTER(AttnParams), vp]),
     "mtts_vq_argmin_f32": (C.c_int, [vp, i32, vp, i64, i32, i32, vp, vp]),

@@ -33,8 +33,41 @@ def slaney_mel_filterbank(n_freqs=HIFIGAN_NFFT // 2 + 1, f_min=0.0, f_max=float(
     return (tri * (2.0 / (right - left))).astype(np.float32)
 
 
+def pack_grouped_filterbank(fb: np.ndarray):
+    """(n_bins, n_mels) dense filterbank -> (fb_w float32, fb_off int32 [G + 1], fb_start int32 [4 G]): the grouped banded
+    form mtts_mel_spectrogram_f32 takes (include/megatts2_b200.h).  Mels go in groups of 4; each mel's band is read from
+    a start bin rounded down to a multiple of 4 (shifted further down where it would run past bin n_bins + 2), for
+    len_g taps = the group's longest aligned band rounded up to a multiple of 4.  A group's block is (4, len_g) row-major
+    with zeros outside a mel's own band - the kernel's tap loop is uniform across the group and uses 128-bit reads."""
+    n_bins, n_mels = fb.shape
+    G = (n_mels + 3) // 4
+    limit = (n_bins + 3) // 4 * 4                        # the kernel zeroes the magnitudes between n_bins and this
+    lo = np.zeros(4 * G, dtype=np.int64)
+    ln = np.zeros(4 * G, dtype=np.int64)
+    for m in range(n_mels):
+        nz = np.nonzero(fb[:, m])[0]
+        if nz.size:
+            lo[m], ln[m] = int(nz[0]), int(nz[-1]) + 1 - int(nz[0])
+    offs, blocks, starts = [0], [], np.zeros(4 * G, dtype=np.int32)
+    padded = np.zeros((limit, n_mels), dtype=np.float32)
+    padded[:n_bins] = fb
+    for g in range(G):
+        ms = range(4 * g, 4 * g + 4)
+        len_g = max(4, max((int(lo[m]) % 4 + int(ln[m]) + 3) // 4 * 4 for m in ms))
+        assert len_g <= limit
+        block = np.zeros((4, len_g), dtype=np.float32)
+        for i, m in enumerate(ms):
+            s0 = min(int(lo[m]) // 4 * 4, limit - len_g)
+            starts[m] = s0
+            if m < n_mels:
+                block[i] = padded[s0:s0 + len_g, m]
+        blocks.append(block.reshape(-1))
+        offs.append(offs[-1] + 4 * len_g)
+    return np.concatenate(blocks), np.asarray(offs, dtype=np.int32), starts
+
+
 class _MelTables:
-    """Window + banded filterbank tables, built once per device."""
+    """Window + grouped banded filterbank tables, built once per device."""
     _cache = {}
 
     @classmethod
@@ -42,21 +75,14 @@ class _MelTables:
         key = (device.type, device.index)
         t = cls._cache.get(key)
         if t is None:
-            fb = slaney_mel_filterbank()                      # (513, 80)
-            offs, starts, weights = [0], [], []
-            for m in range(fb.shape[1]):
-                nz = np.nonzero(fb[:, m])[0]
-                lo, hi = (int(nz[0]), int(nz[-1]) + 1) if nz.size else (0, 0)
-                starts.append(lo)
-                weights.append(fb[lo:hi, m])
-                offs.append(offs[-1] + (hi - lo))
+            fb_w, fb_off, fb_start = pack_grouped_filterbank(slaney_mel_filterbank())      # (513, 80)
             # the exact fp32 table torchaudio's MelSpectrogram uses (window_fn=torch.hann_window, periodic)
             window = torch.hann_window(HIFIGAN_WIN_LENGTH, periodic=True, dtype=torch.float32)
             t = dict(
                 window=window.to(device),
-                fb_w=torch.from_numpy(np.concatenate(weights)).to(device),
-                fb_off=torch.tensor(offs, dtype=torch.int32, device=device),
-                fb_start=torch.tensor(starts, dtype=torch.int32, device=device),
+                fb_w=torch.from_numpy(fb_w).to(device),
+                fb_off=torch.from_numpy(fb_off).to(device),
+                fb_start=torch.from_numpy(fb_start).to(device),
             )
             cls._cache[key] = t
         return t

@@ -7,6 +7,7 @@ import os
 import re
 
 import pytest
+import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -133,13 +134,34 @@ def test_mel_tables_match_oracle():
     fb = torch.from_numpy(tk.slaney_mel_filterbank())
     assert (fb - R.slaney_fbanks()).abs().max() < 1e-7
     t = tk._MelTables.get(torch.device("cpu"))
-    assert t["fb_w"].numel() == 1001 and t["fb_off"][-1] == 1001
-    # banded form reproduces the dense matrix
-    dense = torch.zeros(513, 80)
-    for m in range(80):
-        o0, o1, s0 = int(t["fb_off"][m]), int(t["fb_off"][m + 1]), int(t["fb_start"][m])
-        dense[s0:s0 + (o1 - o0), m] = t["fb_w"][o0:o1]
-    assert torch.equal(dense, fb)
+    assert t["fb_off"].numel() == 21 and t["fb_start"].numel() == 80 and t["fb_w"].numel() == int(t["fb_off"][-1]) <= 1536
+    # the grouped banded form reproduces the dense matrix (reads stay below bin 516, aligned to 4)
+    dense = torch.zeros(516, 80)
+    for g in range(20):
+        o0, o1 = int(t["fb_off"][g]), int(t["fb_off"][g + 1])
+        block = t["fb_w"][o0:o1].reshape(4, -1)
+        assert block.shape[1] % 4 == 0
+        for i in range(4):
+            s0 = int(t["fb_start"][4 * g + i])
+            assert s0 % 4 == 0 and s0 + block.shape[1] <= 516
+            dense[s0:s0 + block.shape[1], 4 * g + i] += block[i]
+    assert torch.equal(dense[:513], fb) and not dense[513:].any()
+    # odd sizes: a mel count that is not a multiple of 4, an empty band, a band touching the last bin
+    odd = np.zeros((40, 6), dtype=np.float32)
+    odd[3:9, 0] = 1.0; odd[38:40, 1] = 2.0; odd[0:1, 3] = 3.0; odd[10:31, 4] = 4.0; odd[35:40, 5] = 5.0
+    w, off, st = tk.pack_grouped_filterbank(odd)
+    rec = np.zeros_like(odd)
+    rec = np.zeros((40, 6), dtype=np.float32)
+    for g in range(2):
+        block = w[off[g]:off[g + 1]].reshape(4, -1)
+        for i in range(4):
+            m = 4 * g + i
+            assert st[m] % 4 == 0 and st[m] + block.shape[1] <= 40
+            if m < 6:
+                rec[st[m]:st[m] + block.shape[1], m] += block[i]
+            else:
+                assert not block[i].any()
+    assert np.array_equal(rec, odd)
     assert torch.equal(t["window"], torch.hann_window(1024))
 
 

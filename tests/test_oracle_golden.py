@@ -207,3 +207,25 @@ def test_wav_framing_round_trip(tmp_path):
         assert w.readframes(1234) == q.tobytes()
     y2, sr2 = audio.read_wav(str(pi))
     assert sr2 == 22050 and np.array_equal(y2, q.astype(np.float32) / 32768.0)
+
+
+def test_vq_train_restatement_replays_reference_fixture():
+    """oracle/ref_vq_train.py reproduces the REAL reference's train-mode VectorQuantization (three steps: k-means init,
+    dead-code expiry, EMA update, straight-through + commitment loss, backward) from the recorded draws."""
+    import numpy as np
+    from oracle import ref_vq_train as RV
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "vq_train.npz"))
+    K, D, B, N, iters, steps = (int(v) for v in g["meta"])
+    cb = RV.Codebook(D, K, kmeans_iters=iters, decay=float(g["decay"]), threshold_ema_dead_code=2)
+    for s in range(steps):
+        x = torch.from_numpy(g[f"s{s}_x"]).requires_grad_(True)
+        kw = {"expire_pick": torch.from_numpy(g[f"s{s}_expire_pick"])}
+        if s == 0:
+            kw["init_indices"] = torch.from_numpy(g["s0_init_indices"])
+        q, ind, loss, used = RV.vq_forward_train(cb, x, float(g["commitment_weight"]), **kw)
+        ((q * torch.from_numpy(g[f"s{s}_wq"])).sum() + 3.0 * loss.sum()).backward()
+        assert used == bool(g[f"s{s}_expired"])
+        assert torch.equal(ind, torch.from_numpy(g[f"s{s}_ind"]))
+        for name, got in (("q", q), ("loss", loss), ("gx", x.grad), ("embed", cb.embed), ("embed_avg", cb.embed_avg),
+                          ("cluster_size", cb.cluster_size)):
+            assert (got.detach() - torch.from_numpy(g[f"s{s}_{name}"])).abs().max().item() <= 1e-6, (s, name)

@@ -67,3 +67,31 @@ def _worker(rank, world, port, n_items):
 @pytest.mark.parametrize("n_items", [5, 8])
 def test_gather_world2_gloo(n_items):
     mp.spawn(_worker, args=(2, _free_port(), n_items), nprocs=2, join=True)
+
+
+def _bcast_worker(rank, world, port):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from megatts2_b200 import vq_train as VT
+        # the codebook buffers after a k-means initialisation differ per worker until rank 0's are broadcast
+        # (EuclideanCodebook.init_embed_ -> distrib.broadcast_tensors, core_vq.py:141-149)
+        bufs = [torch.full((1,), float(rank)), torch.full((4,), 10.0 + rank), torch.full((4, 3), 20.0 + rank),
+                torch.tensor([rank], dtype=torch.int64)]
+        VT.broadcast_buffers(bufs)
+        assert torch.all(bufs[0] == 0) and torch.all(bufs[1] == 10) and torch.all(bufs[2] == 20)
+        assert int(bufs[3]) == rank            # integer buffers are left alone, like the reference
+        if rank == 1:
+            with pytest.raises(RuntimeError):
+                VT.broadcast_buffers(bufs[:2])
+        else:
+            with pytest.raises(RuntimeError):
+                VT.broadcast_buffers(bufs[:3])
+        dist.barrier()
+    finally:
+        dist.destroy_process_group()
+
+
+def test_codebook_buffer_broadcast_world2_gloo():
+    mp.spawn(_bcast_worker, args=(2, _free_port()), nprocs=2, join=True)
