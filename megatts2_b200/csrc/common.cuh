@@ -88,7 +88,7 @@ struct Arena {
 
 __device__ __forceinline__ float act_apply(float v, int act, float slope) {
   if (act == MTTS_ACT_RELU) return fmaxf(v, 0.f);
-  if (act == MTTS_ACT_LEAKY) return v > 0.f ? v : v * slope;
+  if (act == MTTS_ACT_LEAKY) return v > 0.f ? v : v * slope;   // (kept as a select: correct for any slope)
   if (act == MTTS_ACT_TANH) return tanhf(v);
   return v;
 }

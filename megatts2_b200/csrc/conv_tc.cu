@@ -44,7 +44,6 @@ struct ConvTcArgs {
   // split-K (dense layers with too few tiles): work item = (tile, split); partial sums go to `partial`
   int32_t splits; float* partial;
   int32_t fmt; int32_t* ovf;   // operand format of the plane output (== the kernel's own NP) and the f16 range flag
-  int32_t epi_prefetch;        // epilogue requests bias / residual rows one unit ahead (MEGATTS2_TC_EPI_PREFETCH=1; default off, measured neutral)
   int32_t row0;                // first padded row of this conv inside a shared plane buffer (0 for its own planes)
   int32_t bo_mode;             // halo form, diagnostics: 1 = put (addr >> 7) & 7 into the descriptors' base-offset field (WRONG on B200)
 };
@@ -330,68 +329,67 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
   } else if (warp >= 4) {
     // ================= epilogue: 8 warps, two per TMEM lane quarter, 16-column units =================
     // (the small-channel convs are epilogue-bound: per output element there is more CUDA-core work than
-    //  tensor-pipe work, so the epilogue gets as many warps as the register file allows)
+    //  tensor-pipe work, so the epilogue gets as many warps as the register file allows - and its per-tile
+    //  integer work is kept small: the tile index is advanced in mixed radix instead of being re-divided, every
+    //  global address is a per-tile base plus unit / row steps, and the halo form (one K split, no
+    //  transposed-conv shift) drops those paths at compile time)
     constexpr float CS = NP == 2 ? F16X2_INV_SCALE : 1.0f;   // weight of the correction accumulator (exact: a power of two)
     const int ew = warp - 4;                      // 0..7
     const int q = ew & 3;                         // == warp % 4: the TMEM lane quarter this warp may read
     const int half = ew >> 2;                     // which 16-column units of a tile this warp owns
-    // The bias / residual rows of a unit are REQUESTED ONE UNIT AHEAD (across tile boundaries too): a residual row comes
-    // from HBM (~1 us), and requested at the top of its own unit that latency was exposed once per unit - the epilogue of
-    // the residual-carrying layers (HiFi-GAN convs2, out-projection, FF2) took ~2.5x the MMA time of their tiles.
-    struct UnitLd { float4 bv, rv[4]; };
     const int chunk = lane & 3, rsub = lane >> 2;
-    auto unit_ld = [&](int item_, int u_, UnitLd& L) {
-      const int tile_ = item_ / g.splits;
-      const int nb_ = tile_ % num_n, r0_ = tile_ / num_n;
-      const int tb_ = r0_ % num_t, b_ = r0_ / num_t;
-      const int n_ = nb_ * BN + u_ * 16 + chunk * 4;
-      const int tbase_ = tb_ * BM + (int)crank * 128 + q * 32;
-      const bool on = n_ < g.Cout && g.splits == 1;
-      L.bv = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (on && g.bias) L.bv = __ldg(reinterpret_cast<const float4*>(g.bias + n_));
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int tt = tbase_ + i * 8 + rsub;
-        L.rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (on && g.res && tt < g.T && !g.out_shift)
-          L.rv[i] = *reinterpret_cast<const float4*>(g.res + (int64_t)b_ * g.res_sb + (int64_t)tt * g.ldr + n_);
-      }
-    };
-    UnitLd cur, nxt;
-    if (worker < num_tiles) unit_ld(worker, half, cur);
+    const int splits = HALO ? 1 : g.splits;
+    const int64_t out_shift = HALO ? (int64_t)0 : g.out_shift;
+    const bool partial_out = splits > 1;          // raw partial sums; bias / activation / residual run in the reduction kernel
+    const bool has_bias = g.bias != nullptr && !partial_out;
+    const bool has_res = g.res != nullptr && out_shift == 0 && !partial_out;
+    const bool has_acc = g.accumulate != 0 && out_shift == 0 && !partial_out;
+    const bool has_y = g.y != nullptr, has_op = g.op != nullptr;
+    const int64_t ystep = 8 * (int64_t)g.ldy, rstep = 8 * (int64_t)g.ldr, ostep = 8 * (int64_t)g.op_ld;
+    const int64_t pstep = 8 * (int64_t)g.Cout;
+    // work item -> (K split, column block, row block, batch item), walked with stride nworkers
+    int sp, nb, tb, b, d_sp, d_nb, d_tb, d_b;
+    {
+      int c = worker / splits;
+      sp = worker - c * splits;
+      nb = c % num_n; c /= num_n;
+      tb = c % num_t; b = c / num_t;
+      c = nworkers / splits;
+      d_sp = nworkers - c * splits;
+      d_nb = c % num_n; c /= num_n;
+      d_tb = c % num_t; d_b = c / num_t;
+    }
+    // Each unit = this warp's 32 rows x 16 columns.  The accumulators arrive row-per-lane (TMEM lane == row);
+    // writing them out like that would make every global instruction touch 32 different lines, so the unit
+    // is transposed through a padded shared buffer and ALL global traffic of the epilogue (y, residual,
+    // accumulate, operand planes) is issued as 8 rows x 64 contiguous bytes per instruction.
+    float* stg = epi_stage + ew * (32 * 20);
     int it = 0;
     for (int item = worker; item < num_tiles; item += nworkers, ++it) {
-      const int sp = item % g.splits, tile = item / g.splits;
-      const int nb = tile % num_n, r0 = tile / num_n;
-      const int tb = r0 % num_t, b = r0 / num_t;
       const int as = it % NACC, aphase = (it / NACC) & 1;
-      bool waited = false;      // the accumulator wait is deferred until the next unit's global loads are in flight
-      // Each unit = this warp's 32 rows x 16 columns.  The accumulators arrive row-per-lane (TMEM lane == row);
-      // writing them out like that would make every global instruction touch 32 different lines, so the unit
-      // is transposed through a padded shared buffer and ALL global traffic of the epilogue (y, residual,
-      // accumulate, operand planes) is issued as 8 rows x 64 contiguous bytes per instruction.
-      float* stg = epi_stage + ew * (32 * 20);
-      const int t_base = tb * BM + (int)crank * 128 + q * 32;
+      const int t0 = tb * BM + (int)crank * 128 + q * 32 + rsub;          // this lane's rows: t0 + 8 i
+      const int nbase = nb * BN + chunk * 4;
+      const int64_t yo = (int64_t)t0 * g.ldy + nbase;                      // within batch item b
+      const int64_t yb = (int64_t)b * g.y_sb;
+      const int64_t ro = (int64_t)b * g.res_sb + (int64_t)t0 * g.ldr + nbase;
+      const int64_t oo = ((int64_t)b * g.op_tp + g.op_hl + t0) * g.op_ld + nbase;
+      const int64_t po = (((int64_t)sp * g.B + b) * g.T + t0) * g.Cout + nbase;
+      bool waited = false;      // the accumulator wait is deferred until the unit's global loads are in flight
 #pragma unroll 1
       for (int u = half; u < BN / 16; u += 2) {
-        const int n = nb * BN + u * 16 + chunk * 4;
+        const int n = nbase + u * 16;
         const bool ncol = n < g.Cout;                 // Cout % 4 == 0: a 4-wide chunk is all-in or all-out
-        if (g.epi_prefetch) {   // request the NEXT unit's rows (same tile, or the first unit of this warp's next tile)
-          int nitem = item, nu = u + 2;
-          if (nu >= BN / 16) { nitem = item + nworkers; nu = half; }
-          if (nitem < num_tiles) unit_ld(nitem, nu, nxt);
-        } else {
-          unit_ld(item, u, cur);
-        }
-        const float4 bvec = cur.bv;
+        float4 bvec = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (has_bias && ncol) bvec = __ldg(reinterpret_cast<const float4*>(g.bias + n));
         float4 rv[4], ov[4];
+        bool ok[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int tt = t_base + i * 8 + rsub;
-          rv[i] = cur.rv[i];
+          ok[i] = ncol && (t0 + 8 * i) < g.T;
+          rv[i] = make_float4(0.f, 0.f, 0.f, 0.f);
           ov[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (ncol && tt < g.T && !g.out_shift && g.splits == 1 && g.accumulate)
-            ov[i] = *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n);
+          if (has_res && ok[i]) rv[i] = *reinterpret_cast<const float4*>(g.res + ro + i * rstep + u * 16);
+          if (has_acc && ok[i]) ov[i] = *reinterpret_cast<const float4*>(g.y + yb + yo + i * ystep + u * 16);
         }
         if (!waited) {
           mbar_wait(tfull_bar + 8 * as, aphase);
@@ -413,11 +411,10 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const int row = i * 8 + rsub, tt = t_base + row;
-          if (!ncol || tt >= g.T) continue;
-          const float4 a4 = *reinterpret_cast<const float4*>(stg + row * 20 + chunk * 4);
-          if (g.splits > 1) {      // raw partial sums; bias / activation / residual run in the reduction kernel
-            *reinterpret_cast<float4*>(g.partial + (((int64_t)sp * g.B + b) * g.T + tt) * g.Cout + n) = a4;
+          if (!ok[i]) continue;
+          const float4 a4 = *reinterpret_cast<const float4*>(stg + (i * 8 + rsub) * 20 + chunk * 4);
+          if (partial_out) {
+            *reinterpret_cast<float4*>(g.partial + po + i * pstep + u * 16) = a4;
             continue;
           }
           float v[4] = {a4.x + bvec.x, a4.y + bvec.y, a4.z + bvec.z, a4.w + bvec.w};
@@ -429,21 +426,20 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
           v[1] = (v[1] + rv[i].y) * g.out_scale + ov[i].y;
           v[2] = (v[2] + rv[i].z) * g.out_scale + ov[i].z;
           v[3] = (v[3] + rv[i].w) * g.out_scale + ov[i].w;
-          if (g.y) {
-            const int64_t flat = (int64_t)tt * g.ldy + n + g.out_shift;     // out_shift % 4 == 0: all-in or all-out
-            if (flat >= 0 && flat + 4 <= g.ybe)
-              *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + flat) = make_float4(v[0], v[1], v[2], v[3]);
+          if (has_y) {
+            const int64_t flat = yo + i * ystep + u * 16 + out_shift;      // out_shift % 4 == 0: all-in or all-out
+            if (HALO || (flat >= 0 && flat + 4 <= g.ybe))
+              *reinterpret_cast<float4*>(g.y + yb + flat) = make_float4(v[0], v[1], v[2], v[3]);
           }
-          if (g.op) {
+          if (has_op) {
             if (g.op_act != MTTS_ACT_NONE) {
 #pragma unroll
               for (int e = 0; e < 4; ++e) v[e] = act_apply(v[e], g.op_act, g.op_slope);
             }
-            store_planes4(g.op, g.op_stride, ((int64_t)b * g.op_tp + g.op_hl + tt) * g.op_ld + n, v, NP == 2 ? MTTS_TC_F16X2 : MTTS_TC_BF16X3, g.ovf);
+            store_planes4(g.op, g.op_stride, oo + i * ostep + u * 16, v, NP == 2 ? MTTS_TC_F16X2 : MTTS_TC_BF16X3, g.ovf);
           }
         }
         __syncwarp();   // the staging buffer is reused by the next unit
-        if (g.epi_prefetch) cur = nxt;
       }
       if (!waited) {
         mbar_wait(tfull_bar + 8 * as, aphase);
@@ -455,6 +451,17 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         if constexpr (PAIR) mbar_arrive_cluster(mapa_u32(tempty_bar + 8 * as, 0));     // the leader's MMA issuer waits
         else mbar_arrive(tempty_bar + 8 * as);
       }
+      // next work item: (sp, nb, tb, b) += the stride's digits, with carries
+      sp += d_sp;
+      int carry = sp >= splits;
+      sp -= carry ? splits : 0;
+      nb += d_nb + carry;
+      carry = nb >= num_n;
+      nb -= carry ? num_n : 0;
+      tb += d_tb + carry;
+      carry = tb >= num_t;
+      tb -= carry ? num_t : 0;
+      b += d_b + carry;
     }
   }
   tc_fence_before();
@@ -628,7 +635,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int epi_prefetch; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -646,8 +653,6 @@ static const CtcEnv& ctc_env() {
     const char* be = getenv("MEGATTS2_TC_HALO_BO");       // 1: base-offset field set in the row-shifted descriptors (diagnostics)
     e.halo = !(he && he[0] == '0');
     e.halo_bo = be ? atoi(be) : 0;
-    const char* ee = getenv("MEGATTS2_TC_EPI_PREFETCH");
-    e.epi_prefetch = ee ? atoi(ee) : 0;   // measured: no gain (profiles/r2m_epi_prefetch_ab.log)
     return e;
   }();
   return env;
@@ -859,7 +864,8 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   }
   const int b_rows = pair ? BN / 2 : BN;
   // halo form: one K-slab per tap (Cin <= SWB / 2), the activation tile + halo fits the 192-row buffer
-  const bool halo_form = env.halo && !pair && splits == 1 && p.k > 1 && p.Cin <= SWB / 2 && halo + 128 <= CTC_HALO_ROWS &&
+  const bool halo_form = env.halo && !pair && splits == 1 && p.out_shift == 0 && p.k > 1 && p.Cin <= SWB / 2 &&
+                         halo + 128 <= CTC_HALO_ROWS &&   // (the halo kernel's epilogue has no K-split / transposed-conv paths)
                          ((SWB == 64 && BN == 32) || (SWB == 128 && BN == 64)) && p.Cout == BN;
   ConvTcMaps maps;
   for (int q = 0; q < np; ++q) {
@@ -878,7 +884,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.op = reinterpret_cast<__nv_bfloat16*>(p.tc_out_planes); a.op_stride = p.tc_out_plane_stride; a.op_ld = p.tc_out_ld;
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
-  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0; a.epi_prefetch = env.epi_prefetch;
+  a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0;
   if (halo_form) {
     if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 0, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 0, 3, 1>(maps, a, st);
     return np == 2 ? conv_tc_launch<64, 128, 0, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 0, 3, 1>(maps, a, st);

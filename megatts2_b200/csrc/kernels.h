@@ -32,24 +32,25 @@ struct PlanesOut {
 __device__ __forceinline__ void store_planes4(__nv_bfloat16* planes, int64_t plane_stride, int64_t off, const float* v,
                                               int fmt = MTTS_TC_BF16X3, int32_t* ovf = nullptr) {
   if (fmt == MTTS_TC_F16X2) {
-    uint16_t h[2][4];
-    bool bad = false;
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const __half x1 = __float2half_rn(v[e]);                       // +-inf beyond the fp16 range
-      const __half x2 = __float2half_rn((v[e] - __half2float(x1)) * F16X2_SCALE);   // exact difference, exact scaling
-      h[0][e] = __half_as_ushort(x1);
-      h[1][e] = __half_as_ushort(x2);
-      bad |= !(fabsf(v[e]) <= 65504.0f);                             // also NaN
+    // two elements per conversion instruction (cvt.rn.f16x2.f32); the range check is one NaN-propagating max per element
+    const __half2 h01 = __floats2half2_rn(v[0], v[1]), h23 = __floats2half2_rn(v[2], v[3]);   // +-inf beyond the fp16 range
+    const float2 f01 = __half22float2(h01), f23 = __half22float2(h23);
+    const __half2 l01 = __floats2half2_rn((v[0] - f01.x) * F16X2_SCALE, (v[1] - f01.y) * F16X2_SCALE);   // exact difference,
+    const __half2 l23 = __floats2half2_rn((v[2] - f23.x) * F16X2_SCALE, (v[3] - f23.y) * F16X2_SCALE);   // exact scaling
+    uint2 o;
+    o.x = *reinterpret_cast<const uint32_t*>(&h01);
+    o.y = *reinterpret_cast<const uint32_t*>(&h23);
+    *reinterpret_cast<uint2*>(planes + off) = o;
+    o.x = *reinterpret_cast<const uint32_t*>(&l01);
+    o.y = *reinterpret_cast<const uint32_t*>(&l23);
+    *reinterpret_cast<uint2*>(planes + plane_stride + off) = o;
+    if (ovf) {
+      float m;
+      asm("{\n\t.reg .f32 t0, t1, t2, t3;\n\tabs.f32 t0, %1;\n\tabs.f32 t1, %2;\n\tabs.f32 t2, %3;\n\tabs.f32 t3, %4;\n\t"
+          "max.NaN.f32 t0, t0, t1;\n\tmax.NaN.f32 t2, t2, t3;\n\tmax.NaN.f32 %0, t0, t2;\n\t}"
+          : "=f"(m) : "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]));
+      if (!(m <= 65504.0f)) *ovf = 1;                                  // also NaN
     }
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-      uint2 o;
-      o.x = (uint32_t)h[q][0] | ((uint32_t)h[q][1] << 16);
-      o.y = (uint32_t)h[q][2] | ((uint32_t)h[q][3] << 16);
-      *reinterpret_cast<uint2*>(planes + q * plane_stride + off) = o;
-    }
-    if (bad && ovf) *ovf = 1;
     return;
   }
   // bf16x3: round-to-nearest at every step
