@@ -163,6 +163,10 @@ typedef struct {
   int32_t o_planes_fmt;                    /* MTTS_TC_BF16X3 | MTTS_TC_F16X2 */
 } mtts_attn_params;
 int mtts_attention_f32(const mtts_attn_params* p, void* stream);
+/* Opt-in: AR-step attention (Tq == Tk <= 64, even head count, dh 64 | 96) with at least `min_len` rows runs on the
+ * two-heads-per-CTA tcgen05 kernel instead of the fp32 kernel; min_len <= 0 switches it off (the default: it is slower
+ * inside the synthesis step, see csrc/ops.cu).  Returns the previous setting. */
+int mtts_set_attention_pair_min(int32_t min_len);
 
 /* EuclideanCodebook.quantize (modules/quantization/core_vq.py:175-183): first index of
  * max_k -(|x|^2 - 2 x.e_k + |e_k|^2).  x (N, D) ld = ldx, embed (K, D) -> idx (N) int64 */

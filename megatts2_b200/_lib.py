@@ -119,6 +119,7 @@ SIGNATURES = {
     "mtts_split_planes_f32": (C.c_int, [vp, i32, i64, i32, vp, i32, vp]),
     "mtts_tc_overflow_bind": (C.c_int, [vp]),
     "mtts_set_sm_limit": (C.c_int, [i32]),
+    "mtts_set_attention_pair_min": (C.c_int, [i32]),
     "mtts_mask_tail_f32": (C.c_int, [vp, i32, i32, i32, vp, vp]),
     "mtts_resample_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, i32, i32, i32, i32, vp, i64, i32, vp, vp]),
     "mtts_peak_normalize_f32": (C.c_int, [vp, i64, i32, i32, vp, vp, vp]),

@@ -57,7 +57,6 @@ struct ConvTcArgs {
 constexpr int CTC_HALO_ROWS = 192;     // rows of a halo tile buffer: 128 + dil * (k - 1) <= 192, a multiple of 8
 template <int BN, int SWB, int PAIR = 0, int NP = 3, int HALO = 0>
 struct ConvTcCfg {
-  static_assert(!(PAIR && HALO), "the halo form is single-CTA");
   static constexpr int BK = SWB / 2;                       // bf16 elements per swizzled row
   static constexpr int A_PLANE = (HALO ? CTC_HALO_ROWS : 128) * SWB;
   static constexpr int B_ROWS = PAIR ? BN / 2 : BN;        // weight rows staged by one CTA
@@ -169,8 +168,18 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         const int ab = ait % Cfg::A_BUFS, aph = (ait / Cfg::A_BUFS) & 1;
         ++ait;
         mbar_wait(aempty_bar + 8 * ab, aph ^ 1);
-        if (leader) {
-          mbar_expect_tx(afull_bar + 8 * ab, (uint32_t)(NP * (128 + g.dil * (g.k - 1)) * SWB));
+        const uint32_t a_bytes = (uint32_t)(NP * (128 + g.dil * (g.k - 1)) * SWB);
+        if constexpr (PAIR) {
+          // both CTAs' tiles are counted on the LEADER's barrier (the leader issues the MMAs for the pair)
+          const uint32_t fa = mapa_u32(afull_bar + 8 * ab, 0);
+          if (leader) {
+            if (crank == 0) mbar_expect_tx(afull_bar + 8 * ab, 2 * a_bytes);
+#pragma unroll
+            for (int q = 0; q < NP; ++q)
+              tma_load_3d_2sm(smem_a + (ab * NP + q) * Cfg::A_PLANE, &maps.a[q], fa, 0, trow, b);
+          }
+        } else if (leader) {
+          mbar_expect_tx(afull_bar + 8 * ab, a_bytes);
 #pragma unroll
           for (int q = 0; q < NP; ++q)
             tma_load_3d(smem_a + (ab * NP + q) * Cfg::A_PLANE, &maps.a[q], afull_bar + 8 * ab, 0, trow, b);
@@ -178,11 +187,21 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         for (int kb = kb0; kb < kb1; ++kb) {
           mbar_wait(empty_bar + 8 * stage, phase ^ 1);
           const uint32_t sb = smem_base + stage * Cfg::STAGE;
-          const uint32_t fb = full_bar + 8 * stage;
-          if (leader) {
-            mbar_expect_tx(fb, Cfg::STAGE);
+          if constexpr (PAIR) {
+            const uint32_t fb = mapa_u32(full_bar + 8 * stage, 0);
+            if (leader) {
+              if (crank == 0) mbar_expect_tx(full_bar + 8 * stage, 2 * Cfg::STAGE);
 #pragma unroll
-            for (int q = 0; q < NP; ++q) tma_load_2d(sb + q * Cfg::B_PLANE, &maps.b[q], fb, 0, kb * g.Cout + nb * BN);
+              for (int q = 0; q < NP; ++q)
+                tma_load_2d_2sm(sb + q * Cfg::B_PLANE, &maps.b[q], fb, 0, kb * g.Cout + nb * BN + (int)crank * Cfg::B_ROWS);
+            }
+          } else {
+            const uint32_t fb = full_bar + 8 * stage;
+            if (leader) {
+              mbar_expect_tx(fb, Cfg::STAGE);
+#pragma unroll
+              for (int q = 0; q < NP; ++q) tma_load_2d(sb + q * Cfg::B_PLANE, &maps.b[q], fb, 0, kb * g.Cout + nb * BN);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -253,24 +272,47 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
               const uint64_t b1 = desc_base | (uint64_t)((bb >> 4) & 0x3FFF), b2 = desc_base | (uint64_t)(((bb + Cfg::B_PLANE) >> 4) & 0x3FFF);
               const uint32_t f = (ks == 0) ? first : 1u;
               if constexpr (NP == 2) {
-                tc_mma_l(d_corr, a1, b2, idesc, f, leader);
-                tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
-                tc_mma_l(d_main, a1, b1, idesc, f, leader);
+                if constexpr (PAIR) {
+                  tc_mma_2sm_l(d_corr, a1, b2, idesc, f, leader);
+                  tc_mma_2sm_l(d_corr, a2, b1, idesc, 1u, leader);
+                  tc_mma_2sm_l(d_main, a1, b1, idesc, f, leader);
+                } else {
+                  tc_mma_l(d_corr, a1, b2, idesc, f, leader);
+                  tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
+                  tc_mma_l(d_main, a1, b1, idesc, f, leader);
+                }
               } else {
                 const uint64_t a3 = umma_desc_shifted(desc_base, aa + 2 * Cfg::A_PLANE, g.bo_mode);
                 const uint64_t b3 = desc_base | (uint64_t)(((bb + 2 * Cfg::B_PLANE) >> 4) & 0x3FFF);
-                tc_mma_l(d_corr, a2, b2, idesc, f, leader);
-                tc_mma_l(d_corr, a1, b3, idesc, 1u, leader);
-                tc_mma_l(d_corr, a3, b1, idesc, 1u, leader);
-                tc_mma_l(d_corr, a1, b2, idesc, 1u, leader);
-                tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
-                tc_mma_l(d_main, a1, b1, idesc, f, leader);
+                if constexpr (PAIR) {
+                  tc_mma_2sm_l(d_corr, a2, b2, idesc, f, leader);
+                  tc_mma_2sm_l(d_corr, a1, b3, idesc, 1u, leader);
+                  tc_mma_2sm_l(d_corr, a3, b1, idesc, 1u, leader);
+                  tc_mma_2sm_l(d_corr, a1, b2, idesc, 1u, leader);
+                  tc_mma_2sm_l(d_corr, a2, b1, idesc, 1u, leader);
+                  tc_mma_2sm_l(d_main, a1, b1, idesc, f, leader);
+                } else {
+                  tc_mma_l(d_corr, a2, b2, idesc, f, leader);
+                  tc_mma_l(d_corr, a1, b3, idesc, 1u, leader);
+                  tc_mma_l(d_corr, a3, b1, idesc, 1u, leader);
+                  tc_mma_l(d_corr, a1, b2, idesc, 1u, leader);
+                  tc_mma_l(d_corr, a2, b1, idesc, 1u, leader);
+                  tc_mma_l(d_main, a1, b1, idesc, f, leader);
+                }
               }
             }
-            tc_commit_l(empty_bar + 8 * stage, leader);
-            if (kb == kb1 - 1) {
-              tc_commit_l(aempty_bar + 8 * ab, leader);           // the halo tile is free once this tile's MMAs have retired
-              tc_commit_l(tfull_bar + 8 * as, leader);
+            if constexpr (PAIR) {
+              tc_commit_2sm_l(empty_bar + 8 * stage, leader);
+              if (kb == kb1 - 1) {
+                tc_commit_2sm_l(aempty_bar + 8 * ab, leader);       // the halo tiles of both CTAs are free once these MMAs retire
+                tc_commit_2sm_l(tfull_bar + 8 * as, leader);
+              }
+            } else {
+              tc_commit_l(empty_bar + 8 * stage, leader);
+              if (kb == kb1 - 1) {
+                tc_commit_l(aempty_bar + 8 * ab, leader);           // the halo tile is free once this tile's MMAs have retired
+                tc_commit_l(tfull_bar + 8 * as, leader);
+              }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
           }
@@ -635,7 +677,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; bool halo_pair; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -653,6 +695,8 @@ static const CtcEnv& ctc_env() {
     const char* be = getenv("MEGATTS2_TC_HALO_BO");       // 1: base-offset field set in the row-shifted descriptors (diagnostics)
     e.halo = !(he && he[0] == '0');
     e.halo_bo = be ? atoi(be) : 0;
+    const char* hp = getenv("MEGATTS2_TC_HALO_PAIR");
+    e.halo_pair = !(hp && hp[0] == '0');
     return e;
   }();
   return env;
@@ -720,7 +764,7 @@ template <int BN, int SWB, int PAIR, int NP, int HALO = 0>
 static int conv_tc_launch(const ConvTcMaps& maps, const ConvTcArgs& a, cudaStream_t st) {
   using Cfg = ConvTcCfg<BN, SWB, PAIR, NP, HALO>;
   // one bit per instantiation in the per-device table (the max-dynamic-shared-memory attribute is per device)
-  constexpr int slot = HALO ? 24 + (BN == 64 ? 0 : 1) + 2 * (NP == 3 ? 0 : 1)
+  constexpr int slot = HALO ? 24 + (BN == 64 ? 0 : 1) + 2 * (NP == 3 ? 0 : 1) + 4 * PAIR
                             : (BN == 128 ? 0 : BN == 64 ? 1 : 2) + 3 * (SWB == 128 ? 0 : 1) + 6 * PAIR + 12 * (NP == 3 ? 0 : 1);
   static_assert(slot < 32, "attribute slots");
   const int dev = cur_device();
@@ -862,11 +906,20 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
     pair = t256 >= (int64_t)(sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
     if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs
   }
-  const int b_rows = pair ? BN / 2 : BN;
   // halo form: one K-slab per tap (Cin <= SWB / 2), the activation tile + halo fits the 192-row buffer
   const bool halo_form = env.halo && !pair && splits == 1 && p.out_shift == 0 && p.k > 1 && p.Cin <= SWB / 2 &&
                          halo + 128 <= CTC_HALO_ROWS &&   // (the halo kernel's epilogue has no K-split / transposed-conv paths)
                          ((SWB == 64 && BN == 32) || (SWB == 128 && BN == 64)) && p.Cout == BN;
+  // ... as a CTA pair: an N = 32 / 64 MMA costs 41 / 48 cycles whatever its M (128 or 256: 52 cycles, measured with
+  // tools/microbench/mma_floor2.cu), and these layers issue k * Cin / 16 * 3 of them per tile, so one instruction per 256
+  // rows nearly halves the tensor-pipe time of the stages that are bound by exactly that
+  bool halo_pair = false;
+  if (halo_form && env.halo_pair) {
+    const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256);
+    const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
+    halo_pair = t256 >= (int64_t)(sms / 2) * 2 && eff256 >= 0.9 * eff128;
+  }
+  const int b_rows = (pair || halo_pair) ? BN / 2 : BN;
   ConvTcMaps maps;
   for (int q = 0; q < np; ++q) {
     MTTS_TRY(cmap_get(planes + q * plane_stride, (uint64_t)p.Cin, (uint64_t)Tp_map, (uint64_t)p.B, SWB / 2,
@@ -885,6 +938,10 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   a.op_tp = p.tc_out_tp; a.op_hl = p.tc_out_hl; a.op_act = p.tc_out_act; a.op_slope = p.tc_out_slope;
   a.splits = splits; a.partial = reinterpret_cast<float*>(p.tc_partial);
   a.fmt = fmt; a.ovf = ovf; a.bo_mode = env.halo_bo; a.row0 = p.tc_in_row0;
+  if (halo_form && halo_pair) {
+    if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 1, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 1, 3, 1>(maps, a, st);
+    return np == 2 ? conv_tc_launch<64, 128, 1, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 1, 3, 1>(maps, a, st);
+  }
   if (halo_form) {
     if (SWB == 64) return np == 2 ? conv_tc_launch<32, 64, 0, 2, 1>(maps, a, st) : conv_tc_launch<32, 64, 0, 3, 1>(maps, a, st);
     return np == 2 ? conv_tc_launch<64, 128, 0, 2, 1>(maps, a, st) : conv_tc_launch<64, 128, 0, 3, 1>(maps, a, st);

@@ -832,6 +832,7 @@ int mtts_split_planes_f32(const float* x, int32_t ldx, int64_t rows, int32_t C, 
   return split_planes(x, ldx, rows, C, planes, fmt, (cudaStream_t)stream);
 }
 int mtts_tc_overflow_bind(int32_t* flag_dev) { return tc_overflow_bind(flag_dev); }
+int mtts_set_attention_pair_min(int32_t min_len) { return set_attention_pair_min(min_len); }
 int mtts_set_sm_limit(int32_t n_sms) { return set_sm_limit(n_sms); }
 
 int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) { return plm_ws_floats(m, B, T) * 4 + 8192; }

@@ -98,7 +98,10 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
               int ldy, int64_t rows, int C, float eps, int post_act, int accumulate, cudaStream_t st);
 int attention(const mtts_attn_params& p, cudaStream_t st);
 bool attention_tc_eligible(const mtts_attn_params& p);
-int attention_tc(const mtts_attn_params& p, cudaStream_t st);   // tcgen05 (attn_tc.cu)
+int attention_tc(const mtts_attn_params& p, cudaStream_t st);
+bool attention_tc_pair_eligible(const mtts_attn_params& p);
+int attention_tc_pair(const mtts_attn_params& p, cudaStream_t st);
+int set_attention_pair_min(int n);   // tcgen05 (attn_tc.cu)
 int vq_argmin(const float* x, int ldx, const float* embed, int64_t N, int D, int K, int64_t* idx, cudaStream_t st);
 int vq_gather(const int64_t* idx, int idx_ld, const float* embed, int D, int K, int B, int T_out, int repeat, float* y,
               int64_t y_sb, int ldy, cudaStream_t st);

@@ -5,6 +5,8 @@
 #include <math.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "kernels.h"
 
 namespace mtts {
@@ -383,6 +385,12 @@ static int attn_launch(const mtts_attn_params& p, cudaStream_t st) {
   return 0;
 }
 
+static std::atomic<int> g_attn_pair_min{[] {
+  const char* m = getenv("MEGATTS2_ATTN_PAIR_MIN");
+  return m ? atoi(m) : (1 << 30);
+}()};
+int set_attention_pair_min(int n) { return g_attn_pair_min.exchange(n > 0 ? n : (1 << 30), std::memory_order_relaxed); }
+
 int attention(const mtts_attn_params& p, cudaStream_t st) {
   MTTS_REQUIRE(p.q && p.k && p.v && (p.o || p.o_planes), "null pointer");
   MTTS_REQUIRE(!p.o_planes || (p.o_planes_ld % 4 == 0 && p.o_plane_stride % 4 == 0), "plane output alignment");
@@ -402,6 +410,14 @@ int attention(const mtts_attn_params& p, cudaStream_t st) {
       return m ? atoi(m) : 65;
     }();
     if (p.Tq >= tc_min && attention_tc_eligible(p)) return attention_tc(p, st);
+    // AR steps (Tq == Tk <= 64): two heads stacked into one 128-row tile (attn_tc_pair_kernel).  Measured (gpurun call Q,
+    // profiles/r2q_attention_pair_ab.log): in isolation 39.6 vs 52.8 us at S = 64 and 31.0 vs 39.4 us at S = 48 for the PLM
+    // heads, level for the ADM heads (dh 96: one CTA per SM), slower below S = 40; inside the step it LOSES (PLM 151.8 ->
+    // 154.3 ms, ADM 56.3 -> 64.4 ms): the operand conversions, not the MMAs, are what a 64 x 64 x 64 head costs, and its
+    // 97-144 KB / 256 TMEM columns keep the neighbouring GEMMs' CTAs from overlapping.  So it is opt-in
+    // (mtts_set_attention_pair_min / MEGATTS2_ATTN_PAIR_MIN: shortest sequence that takes it), off by default.
+    const int pair_min = g_attn_pair_min.load(std::memory_order_relaxed);
+    if (p.Tq >= pair_min && attention_tc_pair_eligible(p)) return attention_tc_pair(p, st);
   }
   // dh <= 128: one CTA of 8 warps covers a whole AR-step sequence (Tq <= 64), so K and V are read once per (b, h);
   // the rows are dealt evenly to the warps (RW = ceil(Tq / 8) rows each) - with a fixed 8 rows per warp a 35-row

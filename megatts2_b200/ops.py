@@ -323,6 +323,12 @@ def _dev_index(device):
     return torch.cuda.current_device() if device.index is None else device.index
 
 
+def set_attention_pair_min(min_len):
+    """Opt-in two-heads-per-CTA tensor-core attention for AR steps of at least ``min_len`` rows (0 / None: off).
+    Returns the previous setting."""
+    return int(L.lib().mtts_set_attention_pair_min(int(min_len or 0)))
+
+
 def tc_overflow_bind(device):
     """Registers (once per device) the int32 flag the f16x2 operand split raises when an activation leaves the
     fp16 range (|x| > 65504); returns the flag tensor."""

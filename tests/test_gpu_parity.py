@@ -196,9 +196,21 @@ def test_layernorm(C_):
 @pytest.mark.parametrize("H,dh,Tq,Tk", [(16, 64, 70, 70), (8, 96, 33, 33), (2, 256, 12, 12), (1, 512, 64, 31),
                                         (16, 64, 1, 200), (4, 128, 17, 65),
                                         # tensor-core path (attn_tc.cu): one / several query tiles and key tiles, ragged edges
-                                        (16, 64, 64, 64), (16, 64, 130, 300), (8, 96, 200, 200), (8, 96, 16, 16), (2, 128, 129, 64)])
+                                        (16, 64, 64, 64), (16, 64, 130, 300), (8, 96, 200, 200), (8, 96, 16, 16), (2, 128, 129, 64),
+                                        # two heads per CTA (AR steps, Tq == Tk <= 64)
+                                        (16, 64, 24, 24), (16, 64, 47, 47), (8, 96, 64, 64), (2, 64, 40, 40)])
 def test_attention(H, dh, Tq, Tk):
     from megatts2_b200 import ops
+    prev = ops.set_attention_pair_min(16)     # the opt-in two-heads-per-CTA kernel takes the eligible cases
+    try:
+        _attention_cases(ops, H, dh, Tq, Tk)
+    finally:
+        ops.set_attention_pair_min(0 if prev >= (1 << 30) else prev)
+    if Tq == Tk and Tk <= 64 and H % 2 == 0 and dh in (64, 96):
+        _attention_cases(ops, H, dh, Tq, Tk)  # and the default (fp32) kernel
+
+
+def _attention_cases(ops, H, dh, Tq, Tk):
     g = gen(H * 1000 + dh + Tq)
     B, D = 2, H * dh
     q, k, v = (torch.randn(B, t, D, generator=g) for t in (Tq, Tk, Tk))

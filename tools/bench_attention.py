@@ -13,7 +13,7 @@ from megatts2_b200 import ops  # noqa: E402
 def main():
     mode = os.environ.get("MEGATTS2_ATTN_TC", "1")
     for (B, H, dh) in ((64, 16, 64), (64, 8, 96), (16, 16, 64)):
-        for S in (32, 64, 128, 256, 512):
+        for S in [int(x) for x in os.environ.get("BENCH_S", "32,64,128,256,512").split(",")]:
             if B * S > 64 * 256 and B == 64:
                 continue
             qkv = torch.randn(B, S, 3 * H * dh, device="cuda")
@@ -30,7 +30,7 @@ def main():
             torch.cuda.synchronize()
             ms = e0.elapsed_time(e1) / 20
             fl = 4.0 * B * H * S * S * dh
-            print(f"ATTN_TC={mode} B{B} H{H} dh{dh} S{S:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.2f} TFLOP/s", flush=True)
+            print(f"ATTN_TC={mode} PAIR_MIN={os.environ.get('MEGATTS2_ATTN_PAIR_MIN', '24')} B{B} H{H} dh{dh} S{S:4d}: {ms * 1e3:8.1f} us  {fl / ms / 1e9:7.2f} TFLOP/s", flush=True)
 
 
 if __name__ == "__main__":
