@@ -677,7 +677,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; bool halo_pair; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int halo_pair; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -696,7 +696,7 @@ static const CtcEnv& ctc_env() {
     e.halo = !(he && he[0] == '0');
     e.halo_bo = be ? atoi(be) : 0;
     const char* hp = getenv("MEGATTS2_TC_HALO_PAIR");
-    e.halo_pair = !(hp && hp[0] == '0');
+    e.halo_pair = hp ? atoi(hp) : 1;          // 0 off, 1 = the C = 64 stage only (default), 2 = C = 32 too
     return e;
   }();
   return env;
@@ -912,9 +912,11 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
                          ((SWB == 64 && BN == 32) || (SWB == 128 && BN == 64)) && p.Cout == BN;
   // ... as a CTA pair: an N = 32 / 64 MMA costs 41 / 48 cycles whatever its M (128 or 256: 52 cycles, measured with
   // tools/microbench/mma_floor2.cu), and these layers issue k * Cin / 16 * 3 of them per tile, so one instruction per 256
-  // rows nearly halves the tensor-pipe time of the stages that are bound by exactly that
+  // rows nearly halves their tensor-pipe time.  Measured (gpurun calls R, S): C = 64, k = 7: 0.415 -> 0.358 ms; C = 32: 0.424 ->
+  // 0.453 ms (its tiles are paced by the epilogue, not by MMA issue; four accumulator buffers instead of two change nothing
+  // either: call T) - so pairs are the default for the C = 64 stage only (MEGATTS2_TC_HALO_PAIR = 0 | 1 | 2)
   bool halo_pair = false;
-  if (halo_form && env.halo_pair) {
+  if (halo_form && (env.halo_pair >= 2 || (env.halo_pair == 1 && SWB == 128))) {
     const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256);
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
     halo_pair = t256 >= (int64_t)(sms / 2) * 2 && eff256 >= 0.9 * eff128;
