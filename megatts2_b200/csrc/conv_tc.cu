@@ -252,7 +252,38 @@ conv_tc_kernel(const __grid_constant__ ConvTcMaps maps, const ConvTcArgs g) {
         tc_fence_after();
         const uint32_t d_main = tmem_base + as * (2 * BN);
         const uint32_t d_corr = d_main + BN;
-        if constexpr (HALO) {
+        if constexpr (HALO && NP == 2) {
+          // f16x2 halo form: per tap ONE asm block issues the k-steps' MMAs from two base descriptors (tc_tap_f16x2); the
+          // A descriptor advances by dil rows per tap, the B descriptor follows the stage ring - a handful of uniform
+          // instructions per tap instead of ~100
+          const int ab = it % Cfg::A_BUFS, aph = (it / Cfg::A_BUFS) & 1;
+          mbar_wait(afull_bar + 8 * ab, aph);
+          uint64_t a_tap = desc_base | (uint64_t)((smem_a + ab * NP * Cfg::A_PLANE + (uint32_t)(kb0 * g.dil) * SWB) >> 4);
+          const uint64_t a_step = (uint64_t)((uint32_t)(g.dil * SWB) >> 4);
+          for (int kb = kb0; kb < kb1; ++kb) {          // kb == tap (one K-slab per tap)
+            mbar_wait(full_bar + 8 * stage, phase);
+            tc_fence_after();
+            const uint64_t b_tap = desc_base | (uint64_t)((smem_base + stage * Cfg::STAGE) >> 4);
+            tc_tap_f16x2<Cfg::BK / 16, PAIR>(d_main, d_corr, a_tap, b_tap, Cfg::A_PLANE >> 4, Cfg::B_PLANE >> 4, idesc,
+                                             (kb == kb0) ? 0u : 1u, leader);
+            a_tap += a_step;
+            if constexpr (PAIR) {
+              tc_commit_2sm_l(empty_bar + 8 * stage, leader);
+              if (kb == kb1 - 1) {
+                tc_commit_2sm_l(aempty_bar + 8 * ab, leader);       // the halo tiles of both CTAs are free once these MMAs retire
+                tc_commit_2sm_l(tfull_bar + 8 * as, leader);
+              }
+            } else {
+              tc_commit_l(empty_bar + 8 * stage, leader);
+              if (kb == kb1 - 1) {
+                tc_commit_l(aempty_bar + 8 * ab, leader);           // the halo tile is free once this tile's MMAs have retired
+                tc_commit_l(tfull_bar + 8 * as, leader);
+              }
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+          }
+          continue;
+        } else if constexpr (HALO) {
           const int ab = it % Cfg::A_BUFS, aph = (it / Cfg::A_BUFS) & 1;
           mbar_wait(afull_bar + 8 * ab, aph);
           for (int kb = kb0; kb < kb1; ++kb) {          // kb == tap (one K-slab per tap)
@@ -826,7 +857,9 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
   if (p.tc_out_planes && (p.Cout % 32 != 0 || p.tc_out_ld % 4 != 0 || p.tc_out_plane_stride % 4 != 0)) return false;
   if (p.res && (p.ldr % 4 != 0 || p.res_batch_stride % 4 != 0 || (((uintptr_t)p.res) & 15) != 0)) return false;
   if (p.Tout != p.Tin + 2 * p.pad - p.dil * (p.k - 1)) return false;
-  if ((int64_t)p.B * p.Tout < 128) return false;         // tiny problems stay on the exact FFMA engine
+  // tiny problems stay on the exact FFMA engine - except rows that already sit in a plane buffer of >= 128 rows (the last
+  // rows of an AR step: one half-filled tile, K split across the SMs)
+  if ((int64_t)p.B * p.Tout < ((p.tc_presplit && p.tc_rows_cap >= 128) ? 32 : 128)) return false;
   int64_t Tp = p.Tout + p.dil * (p.k - 1);
   if (p.tc_in_tp > 0 || p.tc_in_row0 != 0) {      // shared plane buffer: this conv's rows must lie inside it
     if (!p.tc_presplit || p.tc_rows_cap > 0 || p.tc_in_row0 < 0 || p.tc_in_tp < p.tc_in_row0 + Tp) return false;

@@ -95,6 +95,15 @@ static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int
   return rc;
 }
 
+// MEGATTS2_LAST_ROW_TC=0: the final layer's last-row work stays on the exact FFMA engine (read once)
+static bool last_row_tc() {
+  static const bool on = [] {
+    const char* e = getenv("MEGATTS2_LAST_ROW_TC");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
+
 // dense layer dispatch: one tap-GEMM call; conv1d() picks the tcgen05 engine when planes + scratch are attached
 // and the shape is eligible (M >= 128), else the exact FFMA engine
 static int lin(const mtts_encoder* e, const TcScratch* tc, const float* x, int ldx, int64_t M, int K, int N,
@@ -206,6 +215,18 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       // final layer, last position only (exact: nothing else is consumed downstream)
       ap.q = qkv + (int64_t)(T - 1) * 3 * D; ap.q_sb = (int64_t)T * 3 * D; ap.q_st = 3 * D; ap.Tq = 1;
       if (mask) ap.mask = mask + (int64_t)(T - 1) * mask_sq;
+      if (fused && B >= 32 && last_row_tc()) {
+        // the B last rows as one half-filled 128-row tile on the tensor cores (split-K fills the SMs): the attention rows,
+        // LN2 and FF1 write operand planes like the full-sequence layers.  The exact-FFMA form below took 21 + 5 us per
+        // dense layer at B = 64 (weight streaming through the FP32 pipe), 4 layers per AR step.
+        ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D; ap.o_planes_fmt = tc->fmt;
+        MTTS_TRY(attention(ap, st));
+        MTTS_TRY(lin_planes(tc, Pa, B, D, D, L.w_o_tc, L.b_o, xin + (int64_t)(T - 1) * D, T * D, y, D, 0, nullptr, 0, st, part, part_bytes));
+        MTTS_TRY(layernorm_ex(y, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, B, D, 1e-5f, 0, 0, pa_out, st));
+        MTTS_TRY(lin_planes(tc, Pa, B, D, F, L.w_ff1_tc, L.b_ff1, nullptr, 0, nullptr, 0, MTTS_ACT_RELU, Pb, F, st, part, part_bytes));
+        MTTS_TRY(lin_planes(tc, Pb, B, F, D, L.w_ff2_tc, L.b_ff2, y, D, y, D, 0, nullptr, 0, st, part, part_bytes));
+        continue;
+      }
       ap.o = a; ap.o_sb = D; ap.o_st = D;
       MTTS_TRY(attention(ap, st));
       mtts_conv_params p;

@@ -190,4 +190,68 @@ __device__ __forceinline__ uint64_t umma_desc_shifted(uint64_t desc_base, uint32
   return d;
 }
 
+// One tap of the f16x2 halo form: NKS k-steps x three MMAs (x1 w2' and x2' w1 into the correction accumulator, x1 w1 into
+// the main one), issued from ONE asm block whose operand descriptors are derived inside it by 64-bit adds from the two
+// base descriptors.  Written this way because, given one asm statement per MMA with four 64-bit operands each, ptxas
+// re-materialises and re-pairs the (identical) high words and the instruction descriptor for every instruction: ~104
+// uniform-datapath instructions per tap, which - not the tensor pipe - paced the C = 32 / 64 vocoder convolutions
+// (ncu source page of the issuing warp, gpurun call P).
+//   a1 / b1: descriptors of plane 0 at k-step 0; a_plane16 / b_plane16: plane stride >> 4; first: 0 to overwrite the
+//   accumulators with the first k-step (the tile's first tap), else accumulate
+template <int NKS, int PAIR>
+__device__ __forceinline__ void tc_tap_f16x2(uint32_t d_main, uint32_t d_corr, uint64_t a1, uint64_t b1, uint32_t a_plane16,
+                                             uint32_t b_plane16, uint32_t idesc, uint32_t first, uint32_t leader) {
+  static_assert(NKS == 2 || NKS == 4, "k-steps per K-slab");
+#define MTTS_MMA_CG1 "tcgen05.mma.cta_group::1.kind::f16"
+#define MTTS_MMA_CG2 "tcgen05.mma.cta_group::2.kind::f16"
+#define MTTS_TAP_BODY(MMA)                                                                     \
+  "{\n\t"                                                                                      \
+  ".reg .pred p, q, t;\n\t"                                                                    \
+  ".reg .b64 a2, b2, ap, bp;\n\t"                                                              \
+  "setp.ne.b32 p, %6, 0;\n\t"                                                                  \
+  "setp.ne.b32 q, %7, 0;\n\t"                                                                  \
+  "setp.eq.b32 t, 0, 0;\n\t"                                                                   \
+  "cvt.u64.u32 ap, %4;\n\t"                                                                    \
+  "cvt.u64.u32 bp, %5;\n\t"                                                                    \
+  "add.s64 a2, %2, ap;\n\t"                                                                    \
+  "add.s64 b2, %3, bp;\n\t"                                                                    \
+  "@q " MMA " [%1], %2, b2, %8, p;\n\t"                                                        \
+  "@q " MMA " [%1], a2, %3, %8, t;\n\t"                                                        \
+  "@q " MMA " [%0], %2, %3, %8, p;\n\t"
+#define MTTS_TAP_STEP(MMA, OFF)                                                                \
+  "{\n\t"                                                                                      \
+  ".reg .b64 a1k, b1k, a2k, b2k;\n\t"                                                          \
+  "add.s64 a1k, %2, " #OFF ";\n\t"                                                             \
+  "add.s64 b1k, %3, " #OFF ";\n\t"                                                             \
+  "add.s64 a2k, a2, " #OFF ";\n\t"                                                             \
+  "add.s64 b2k, b2, " #OFF ";\n\t"                                                             \
+  "@q " MMA " [%1], a1k, b2k, %8, t;\n\t"                                                      \
+  "@q " MMA " [%1], a2k, b1k, %8, t;\n\t"                                                      \
+  "@q " MMA " [%0], a1k, b1k, %8, t;\n\t"                                                      \
+  "}\n\t"
+  if constexpr (NKS == 2) {
+    if constexpr (PAIR)
+      asm volatile(MTTS_TAP_BODY(MTTS_MMA_CG2) MTTS_TAP_STEP(MTTS_MMA_CG2, 2) "}"
+                   ::"r"(d_main), "r"(d_corr), "l"(a1), "l"(b1), "r"(a_plane16), "r"(b_plane16), "r"(first), "r"(leader), "r"(idesc)
+                   : "memory");
+    else
+      asm volatile(MTTS_TAP_BODY(MTTS_MMA_CG1) MTTS_TAP_STEP(MTTS_MMA_CG1, 2) "}"
+                   ::"r"(d_main), "r"(d_corr), "l"(a1), "l"(b1), "r"(a_plane16), "r"(b_plane16), "r"(first), "r"(leader), "r"(idesc)
+                   : "memory");
+  } else {
+    if constexpr (PAIR)
+      asm volatile(MTTS_TAP_BODY(MTTS_MMA_CG2) MTTS_TAP_STEP(MTTS_MMA_CG2, 2) MTTS_TAP_STEP(MTTS_MMA_CG2, 4) MTTS_TAP_STEP(MTTS_MMA_CG2, 6) "}"
+                   ::"r"(d_main), "r"(d_corr), "l"(a1), "l"(b1), "r"(a_plane16), "r"(b_plane16), "r"(first), "r"(leader), "r"(idesc)
+                   : "memory");
+    else
+      asm volatile(MTTS_TAP_BODY(MTTS_MMA_CG1) MTTS_TAP_STEP(MTTS_MMA_CG1, 2) MTTS_TAP_STEP(MTTS_MMA_CG1, 4) MTTS_TAP_STEP(MTTS_MMA_CG1, 6) "}"
+                   ::"r"(d_main), "r"(d_corr), "l"(a1), "l"(b1), "r"(a_plane16), "r"(b_plane16), "r"(first), "r"(leader), "r"(idesc)
+                   : "memory");
+  }
+#undef MTTS_TAP_STEP
+#undef MTTS_TAP_BODY
+#undef MTTS_MMA_CG2
+#undef MTTS_MMA_CG1
+}
+
 }  // namespace mtts
