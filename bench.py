@@ -422,6 +422,16 @@ def measured_traffic():
     return d.get("dominant_kernel_dram_bytes_per_launch"), d.get("note", "profiles/r2_traffic.json")
 
 
+def mel_traffic(args):
+    """Measured DRAM bytes of one mel_kernel launch on config C2 (ncu capture committed under profiles/); only valid for the
+    default 10 000 clips."""
+    p = os.path.join(ROOT, "profiles", "r2_traffic.json")
+    if args.clips != 10000 or not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f).get("mel_kernel_dram_bytes_per_launch")
+
+
 def cpu_check(args, gpu, lo, revocode):
     """The oracle port (CPU restatement of the reference, batch 1 like the reference) run by concurrent workers on this
     box's host cores over `check_utts` utterances of this rank's batch: it is the CHECKER of the GPU arm's prosody ids /
@@ -617,7 +627,7 @@ def run_c2(args):
                     "d2h_bytes_per_step": int(mel.numel()) * 4},
             "gpu_launches": int(launches), "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "mel_kernel", "achieved": round(gbs, 1), "peak": pk["hbm_gbs"], "unit": "GB/s",
-                         "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": None, "peak_source": pk_src,
+                         "frac": round(gbs / pk["hbm_gbs"], 4), "traffic": mel_traffic(args), "peak_source": pk_src,
                          "algorithmic_bytes_per_clip": bytes_per_clip},
             "cpu_baseline": cpu}
 
