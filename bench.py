@@ -341,8 +341,10 @@ def run_b200(args):
         # ---- roofline leg: per-launch CUDA events around every tap-GEMM launch of ONE step
         # (single stream for this leg: with the prompt re-vocode overlapped on its side stream the per-launch times of two
         #  concurrently running kernels would be summed)
+        from megatts2_b200 import graphs
         lib.mtts_profile_begin()
-        gpu_step(tts, wav_d, phone_d, forced_d, revocode, overlap=False)
+        with graphs.disabled():            # the profile records events between launches: eager enqueue, no graph replay
+            gpu_step(tts, wav_d, phone_d, forced_d, revocode, overlap=False)
         gms, gfl, gn = C.c_double(), C.c_double(), C.c_int64()
         L.check(lib.mtts_profile_end(C.byref(gms), C.byref(gfl), C.byref(gn)))
         log(f"roofline leg: {gn.value} tap-GEMM launches, {gms.value:.1f} ms, {gfl.value / 1e12:.2f} TFLOP")

@@ -147,12 +147,20 @@ class MegaPLM(pack.PlanMixin, nn.Module):
         B, T, _ = tc.shape
         pl = self._plan_get(tc.device, T)
         lib = L.lib()
-        codes = torch.empty(B, T, dtype=torch.int64, device=tc.device)
-        logits = torch.empty(B, T, self.vq_bins, dtype=torch.float32, device=tc.device) if return_logits else None
-        ws = ops.workspace(lib.mtts_plm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
-        L.check(lib.mtts_plm_infer_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
-                                       codes.data_ptr(), logits.data_ptr() if return_logits else None,
-                                       ws.data_ptr(), ws.numel(), ops._stream()))
+
+        def run(tc_):
+            codes = torch.empty(B, T, dtype=torch.int64, device=tc_.device)
+            logits = torch.empty(B, T, self.vq_bins, dtype=torch.float32, device=tc_.device) if return_logits else None
+            ws = ops.workspace(lib.mtts_plm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc_.device)
+            L.check(lib.mtts_plm_infer_f32(C.byref(pl.struct), tc_.data_ptr(), tc_.stride(0), tc_.stride(1), B, T,
+                                           codes.data_ptr(), logits.data_ptr() if return_logits else None,
+                                           ws.data_ptr(), ws.numel(), ops._stream()))
+            return (codes, logits) if return_logits else (codes,)
+
+        # the whole decode is one device-side enqueue sequence: replayed as a CUDA graph from the second call on
+        out = self._graphs().run(("plm", pl.serial, B, T, bool(return_logits), tc.stride(0), tc.stride(1)), (tc,), run)
+        codes = out[0]
+        logits = out[1] if return_logits else None
         return (codes, logits) if return_logits else codes
 
     def infer_causal(self, tc_latent: torch.Tensor, return_logits: bool = False):
@@ -253,12 +261,19 @@ class MegaADM(pack.PlanMixin, nn.Module):
         B, T, _ = tc.shape
         pl = self._plan_get(tc.device, T)
         lib = L.lib()
-        dur = torch.empty(B, T, dtype=torch.int32, device=tc.device)
-        raw = torch.empty(B, T, dtype=torch.float32, device=tc.device) if return_raw else None
-        ws = ops.workspace(lib.mtts_adm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc.device)
-        L.check(lib.mtts_adm_infer_f32(C.byref(pl.struct), tc.data_ptr(), tc.stride(0), tc.stride(1), B, T,
-                                       dur.data_ptr(), raw.data_ptr() if return_raw else None,
-                                       ws.data_ptr(), ws.numel(), ops._stream()))
+
+        def run(tc_):
+            dur = torch.empty(B, T, dtype=torch.int32, device=tc_.device)
+            raw = torch.empty(B, T, dtype=torch.float32, device=tc_.device) if return_raw else None
+            ws = ops.workspace(lib.mtts_adm_infer_workspace_bytes(C.byref(pl.struct), B, T), tc_.device)
+            L.check(lib.mtts_adm_infer_f32(C.byref(pl.struct), tc_.data_ptr(), tc_.stride(0), tc_.stride(1), B, T,
+                                           dur.data_ptr(), raw.data_ptr() if return_raw else None,
+                                           ws.data_ptr(), ws.numel(), ops._stream()))
+            return (dur, raw) if return_raw else (dur,)
+
+        out = self._graphs().run(("adm", pl.serial, B, T, bool(return_raw), tc.stride(0), tc.stride(1)), (tc,), run)
+        dur = out[0]
+        raw = out[1] if return_raw else None
         dur = dur.unsqueeze(-1)
         return (dur, raw) if return_raw else dur
 

@@ -371,5 +371,13 @@ def workspace(nbytes, device):
     return buf
 
 
-def launch_count():
+def _lib_launch_count():
     return int(L.lib().mtts_launch_count())
+
+
+def launch_count():
+    """Kernels launched by this process so far: the library's enqueue counter plus the kernel nodes executed by CUDA-graph
+    replays (megatts2_b200/graphs.py).  A capture pass is counted by the library although it only records - once per graph,
+    during warm-up."""
+    from . import graphs
+    return _lib_launch_count() + graphs.replayed_launches

@@ -242,15 +242,28 @@ class PlanMixin:
     def __getstate__(self):
         d = self.__dict__.copy()
         d["_plan"] = None
+        d.pop("_graph_cache", None)
         return d
+
+    def _graphs(self):
+        """CUDA-graph cache of this module's device-only drivers (megatts2_b200/graphs.py)."""
+        g = self.__dict__.get("_graph_cache")
+        if g is None:
+            from . import graphs
+            g = self.__dict__["_graph_cache"] = graphs.GraphedCall()
+        return g
 
 
 class Plan:
     """Keeps packed device tensors and the ctypes structs that point at them alive together."""
 
+    _serial = 0
+
     def __init__(self):
         self.keep = []
         self.sig = None
+        Plan._serial += 1
+        self.serial = Plan._serial          # identifies THIS packing in graph-cache keys (id() values get reused)
 
     def hold(self, t):
         self.keep.append(t)

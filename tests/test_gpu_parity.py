@@ -503,6 +503,26 @@ def test_prompt_revocode_and_synthesize_many(weights_cpu):
     assert torch.equal(w[0, :, :48 * 256], pw[0, :, :48 * 256]) and float(w[0, :, 48 * 256:].abs().max()) == 0.0
 
 
+def test_graph_replay_matches_eager(PLM, ADM):
+    """The AR drivers replayed from a CUDA graph (megatts2_b200/graphs.py: eager call, capture, replays) give the eager
+    enqueue's ids / durations bit for bit, for new inputs too, and the replayed kernels are counted."""
+    from megatts2_b200 import graphs, ops
+    tc8 = F.relu(torch.randn(4, 12, 512, generator=gen(61))).to(DEV)
+    tc8b = F.relu(torch.randn(4, 12, 512, generator=gen(62))).to(DEV)
+    with graphs.disabled():
+        ref_a, ref_b = PLM.infer(tc8), PLM.infer(tc8b)
+        dref_a, dref_b = ADM.infer(tc8, return_raw=True), ADM.infer(tc8b, return_raw=True)
+    PLM._graphs().clear(); ADM._graphs().clear()
+    n0 = graphs.replayed_launches
+    outs = [PLM.infer(tc8), PLM.infer(tc8), PLM.infer(tc8b), PLM.infer(tc8)]          # eager, capture + replay, replays
+    assert all(torch.equal(o, r) for o, r in zip(outs, (ref_a, ref_a, ref_b, ref_a)))
+    douts = [ADM.infer(tc8, return_raw=True), ADM.infer(tc8, return_raw=True), ADM.infer(tc8b, return_raw=True)]
+    for (d, r), (dr, rr) in zip(douts, (dref_a, dref_a, dref_b)):
+        assert torch.equal(d, dr) and torch.equal(r, rr)
+    if graphs.enabled():
+        assert graphs.replayed_launches > n0 and any(len(e) == 4 for e in PLM._graphs().cache.values())
+
+
 def test_batch_invariance_property(weights_cpu, PLM):
     """Sharding property behind the multi-GPU split: any sub-batch gives bit-identical ids."""
     tc8 = F.relu(torch.randn(8, 16, 512, generator=gen(51))).to(DEV)

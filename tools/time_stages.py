@@ -58,8 +58,10 @@ def main():
     import ctypes as C
     from megatts2_b200 import _lib as L
     lib = L.lib()
+    from megatts2_b200 import graphs
     lib.mtts_trace_begin(ops._stream())
-    bench.gpu_step(tts, wav, phone, forced)
+    with graphs.disabled():                 # the trace records events between launches
+        bench.gpu_step(tts, wav, phone, forced)
     buf = C.create_string_buffer(16384)
     lib.mtts_trace_end(buf, 16384)
     say("== per-launcher event trace of one step (event overhead included)")
