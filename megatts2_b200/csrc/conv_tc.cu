@@ -592,6 +592,82 @@ tc_splitk_reduce_kernel(const ConvTcArgs g, int64_t total4) {
   }
 }
 
+// split-K reduction + LayerNorm of the finished rows (one warp per row, Cout = 128 * NV): the row is reduced exactly like
+// tc_splitk_reduce_kernel does (same order of the partial sums, bias -> activation -> residual -> scale -> accumulate), stored
+// as fp32, and - still in registers - normalised exactly like layernorm_reg_kernel (ops.cu) and written as operand planes.
+// Bit-identical to the two separate launches it replaces.
+template <int NV>
+__global__ void __launch_bounds__(256)
+tc_splitk_reduce_ln_kernel(const ConvTcArgs g, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                           const PlanesOut po) {
+  pdl_entry();
+  constexpr int C = 128 * NV;
+  const int lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);      // b * T + t
+  if (row >= (int64_t)g.B * g.T) return;
+  const int b = (int)(row / g.T), tt = (int)(row - (int64_t)b * g.T);
+  const int64_t stride = (int64_t)g.B * g.T * C;
+  float4 v[NV];
+  // partial sums: split 0, then + split 1, + split 2 ... per element (the order of tc_splitk_reduce_kernel); the NV loads of
+  // one split are independent and in flight together
+  const float* pr = g.partial + row * C + lane * 4;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) v[i] = *reinterpret_cast<const float4*>(pr + i * 128);
+  for (int sp = 1; sp < g.splits; ++sp) {
+    float4 q[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) q[i] = *reinterpret_cast<const float4*>(pr + sp * stride + i * 128);
+#pragma unroll
+    for (int i = 0; i < NV; ++i) { v[i].x += q[i].x; v[i].y += q[i].y; v[i].z += q[i].z; v[i].w += q[i].w; }
+  }
+  {
+    float4 bvv[NV], rvv[NV], ovv[NV];
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int n = i * 128 + lane * 4;
+      bvv[i] = g.bias ? __ldg(reinterpret_cast<const float4*>(g.bias + n)) : make_float4(0.f, 0.f, 0.f, 0.f);
+      rvv[i] = g.res ? *reinterpret_cast<const float4*>(g.res + (int64_t)b * g.res_sb + (int64_t)tt * g.ldr + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+      ovv[i] = g.accumulate ? *reinterpret_cast<const float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int n = i * 128 + lane * 4;
+      float w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      if (g.bias) { w[0] += bvv[i].x; w[1] += bvv[i].y; w[2] += bvv[i].z; w[3] += bvv[i].w; }
+      if (g.post_act != MTTS_ACT_NONE) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) w[e] = act_apply(w[e], g.post_act, g.post_slope);
+      }
+      v[i] = make_float4((w[0] + rvv[i].x) * g.out_scale + ovv[i].x, (w[1] + rvv[i].y) * g.out_scale + ovv[i].y,
+                         (w[2] + rvv[i].z) * g.out_scale + ovv[i].z, (w[3] + rvv[i].w) * g.out_scale + ovv[i].w);
+      *reinterpret_cast<float4*>(g.y + (int64_t)b * g.y_sb + (int64_t)tt * g.ldy + n) = v[i];
+    }
+  }
+  // ---- LayerNorm of the row (the arithmetic of layernorm_reg_kernel, operation for operation)
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float a = v[i].x - mean, bb = v[i].y - mean, d = v[i].z - mean, e = v[i].w - mean;
+    q += (a * a + bb * bb) + (d * d + e * e);
+  }
+  const float rstd = 1.0f / sqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int c = i * 128 + lane * 4;
+    const float4 gm = __ldg(reinterpret_cast<const float4*>(gamma + c));
+    const float4 bt = __ldg(reinterpret_cast<const float4*>(beta + c));
+    float o[4] = {(v[i].x - mean) * rstd * gm.x + bt.x, (v[i].y - mean) * rstd * gm.y + bt.y,
+                  (v[i].z - mean) * rstd * gm.z + bt.z, (v[i].w - mean) * rstd * gm.w + bt.w};
+#pragma unroll
+    for (int e = 0; e < 4; ++e) o[e] = act_apply(o[e], po.act, po.slope);
+    store_planes4(po.p, po.stride, row * po.ld + c, o, po.fmt, po.ovf);
+  }
+}
+
 // fp32 (B,T,C) -> operand planes (B, Tp = T + hl + hr, C): padding materialised, pre-activation applied
 __global__ void __launch_bounds__(256)
 split_pad_kernel(const float* __restrict__ x, int64_t x_sb, int ldx, int T, int C, int hl, int Tp, int pad_mode,
@@ -873,7 +949,8 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
   return 3 * rows * p.Cin * 2 + 2048 <= p.tc_scratch_bytes;
 }
 
-int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
+int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
+  if (ln) ln->done = 0;
   const CtcEnv& env = ctc_env();
   const int sms = cur_device_sms();
   const int fmt = p.tc_fmt;
@@ -983,6 +1060,18 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st) {
   }
   if (splits > 1) {
     MTTS_TRY(np == 2 ? (conv_tc_launch<128, 128, 0, 2>(maps, a, st)) : (conv_tc_launch<128, 128, 0, 3>(maps, a, st)));
+    // the rows' LayerNorm rides on the reduction when the caller asked for it and a row is 3 / 4 / 6 / 8 x 128 wide
+    if (ln && ln->po.p && a.y && !a.op && a.out_shift == 0 && (p.Cout == 1024 || p.Cout == 768 || p.Cout == 512 || p.Cout == 384) &&
+        p.ldy % 4 == 0 && ln->po.ld % 4 == 0 && ln->po.stride % 4 == 0) {
+      const unsigned grid = (unsigned)cdiv64((int64_t)p.B * p.Tout, 4);      // 4 rows (warps) per CTA
+      if (p.Cout == 1024) launch_k(tc_splitk_reduce_ln_kernel<8>, grid, 128, 0, st, a, ln->gamma, ln->beta, ln->eps, ln->po);
+      else if (p.Cout == 768) launch_k(tc_splitk_reduce_ln_kernel<6>, grid, 128, 0, st, a, ln->gamma, ln->beta, ln->eps, ln->po);
+      else if (p.Cout == 512) launch_k(tc_splitk_reduce_ln_kernel<4>, grid, 128, 0, st, a, ln->gamma, ln->beta, ln->eps, ln->po);
+      else launch_k(tc_splitk_reduce_ln_kernel<3>, grid, 128, 0, st, a, ln->gamma, ln->beta, ln->eps, ln->po);
+      MTTS_CHECK_LAUNCH();
+      ln->done = 1;
+      return 0;
+    }
     const int64_t total4 = (int64_t)p.B * p.Tout * p.Cout / 4;
     launch_k(tc_splitk_reduce_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, a, total4);
     MTTS_CHECK_LAUNCH();

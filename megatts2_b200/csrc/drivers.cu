@@ -67,7 +67,7 @@ static inline void tc_partial_area(const mtts_encoder* e, const TcScratch* tc, v
 static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int K, int N, const void* wtc,
                       const float* bias, const float* res, int ldr, float* y, int ldy, int post_act,
                       __nv_bfloat16* out_planes, int out_ld, cudaStream_t st, void* partial = nullptr,
-                      int64_t partial_bytes = 0) {
+                      int64_t partial_bytes = 0, LnFuse* ln = nullptr) {
   mtts_conv_params p = linear_params(nullptr, K, nullptr, bias, y, ldy, M, K, N);
   p.res = res; p.ldr = ldr; p.post_act = post_act;
   p.tc_partial = partial; p.tc_partial_bytes = partial_bytes;
@@ -86,13 +86,22 @@ static int lin_planes(const TcScratch* tc, __nv_bfloat16* planes, int64_t M, int
     r.flops = 2.0 * (double)M * N * K; r.tc = true;
     cudaEventRecord(r.a, st);
   }
-  const int rc = conv_tc(p, st);
+  const int rc = conv_tc(p, st, ln);
   if (prof) {
     cudaEventRecord(r.b, st);
     std::lock_guard<std::mutex> lk(g_prof_mu);
     g_prof.push_back(r);
   }
   return rc;
+}
+
+// MEGATTS2_LN_FUSE=0: LayerNorm always as its own launch (read once)
+static bool ln_fuse() {
+  static const bool on = [] {
+    const char* e = getenv("MEGATTS2_LN_FUSE");
+    return !(e && e[0] == '0');
+  }();
+  return on;
 }
 
 // MEGATTS2_LAST_ROW_TC=0: the final layer's last-row work stays on the exact FFMA engine (read once)
@@ -158,11 +167,14 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
   void* part = nullptr;
   int64_t part_bytes = 0;
   if (fused) tc_partial_area(e, tc, &part, &part_bytes);
+  bool ln1_done = false;     // LN1 of the current layer was produced by the previous layer's split-K reduction
   for (int l = 0; l < e->n_layers; ++l) {
     const mtts_encoder_layer& L = e->layers[l];
     const bool last = last_row_only && (l == e->n_layers - 1);
     if (fused) {
-      MTTS_TRY(layernorm_ex(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
+      // (when the previous layer's FF2 was a split-K launch its reduction already normalised these rows into P_a)
+      if (!ln1_done) MTTS_TRY(layernorm_ex(xin, D, L.ln1_g, L.ln1_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
+      ln1_done = false;
       MTTS_TRY(lin_planes(tc, Pa, M, D, 3 * D, L.w_qkv_tc, L.b_qkv, nullptr, 0, qkv, 3 * D, 0, nullptr, 0, st, part, part_bytes));
     } else {
       // h = LN1(x);  qkv = h Wqkv + b
@@ -180,11 +192,19 @@ static int encoder_forward(const mtts_encoder* e, const float* x, float* y, int 
       if (fused) {
         ap.o = nullptr; ap.o_planes = Pa; ap.o_plane_stride = tc->rows_cap * (int64_t)D; ap.o_planes_ld = D; ap.o_planes_fmt = tc->fmt;
         MTTS_TRY(attention(ap, st));
-        MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st, part, part_bytes));
-        MTTS_TRY(layernorm_ex(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
+        // out-projection (+ residual); a split-K launch's reduction kernel applies LN2 to the finished rows as well
+        LnFuse ln2{L.ln2_g, L.ln2_b, 1e-5f, pa_out, 0};
+        MTTS_TRY(lin_planes(tc, Pa, M, D, D, L.w_o_tc, L.b_o, xin, D, xw, D, 0, nullptr, 0, st, part, part_bytes, ln_fuse() ? &ln2 : nullptr));
+        if (!ln2.done) MTTS_TRY(layernorm_ex(xw, D, L.ln2_g, L.ln2_b, nullptr, 0, nullptr, 0, M, D, 1e-5f, 0, 0, pa_out, st));
         // FF1: relu(h W1 + b1) goes straight to planes P_b; FF2 reads them
         MTTS_TRY(lin_planes(tc, Pa, M, D, F, L.w_ff1_tc, L.b_ff1, nullptr, 0, nullptr, 0, MTTS_ACT_RELU, Pb, F, st, part, part_bytes));
-        MTTS_TRY(lin_planes(tc, Pb, M, F, D, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, nullptr, 0, st, part, part_bytes));
+        // FF2 (+ residual); likewise the NEXT layer's LN1 (all rows are consumed by it unless that layer is the pruned last one
+        // - its LN1 still runs over all rows, only its later stages use the last row)
+        const bool next_ln = l + 1 < e->n_layers;
+        LnFuse ln1{next_ln ? e->layers[l + 1].ln1_g : nullptr, next_ln ? e->layers[l + 1].ln1_b : nullptr, 1e-5f, pa_out, 0};
+        MTTS_TRY(lin_planes(tc, Pb, M, F, D, L.w_ff2_tc, L.b_ff2, xw, D, xw, D, 0, nullptr, 0, st, part, part_bytes,
+                            (next_ln && ln_fuse()) ? &ln1 : nullptr));
+        ln1_done = ln1.done != 0;
         xin = xw;
         continue;
       }

@@ -83,7 +83,15 @@ int layernorm_ex(const float* x, int ldx, const float* gamma, const float* beta,
 int conv1d_ffma(const mtts_conv_params& p, cudaStream_t st);
 int conv1d(const mtts_conv_params& p, cudaStream_t st);   // engine dispatch (FFMA today)
 bool conv_tc_eligible(const mtts_conv_params& p);
-int conv_tc(const mtts_conv_params& p, cudaStream_t st);
+// Optional LayerNorm of the rows a split-K tap-GEMM has just reduced (the dense layers of the AR loops' early steps): the
+// reduction kernel then also normalises each finished row and writes the next layer's operand planes, which saves the
+// separate LayerNorm launch.  `done` is set when the fused kernel ran; the caller launches LayerNorm itself otherwise.
+struct LnFuse {
+  const float* gamma; const float* beta; float eps;
+  PlanesOut po;
+  int done;
+};
+int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln = nullptr);
 int halo_fill(void* planes_base, int B, int T, int C, int hl, int hr, int pad_mode, cudaStream_t st);
 int64_t linear_tc_scratch_bytes(int64_t rows_cap, int K);
 int linear_tc(const float* x, int ldx, int64_t M, int K, const void* w_planes, int N, const float* bias,

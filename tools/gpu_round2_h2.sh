@@ -1,6 +1,9 @@
 #!/bin/bash
+# GPU call H2: LayerNorm fused into the split-K reduction of the preceding dense layer: parity, A/B in the step
 set -u
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_train.py tests/test_gpu_tc.py -q --timeout 600 -p no:randomly -k "train or hifigan or oracle_autograd or functions" 2>&1 | tee gpurun_out/r2h2_pytest.log | tail -12
-MEGATTS2_PDL=1 timeout 600 python tools/time_stages.py --reps 2 2>&1 | tee gpurun_out/r2h2_stages.log | grep -A13 "pass 1"
-bash tools/gpu_round2_i.sh
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 -p no:randomly -x 2>&1 | tail -4
+for rep in 1 2 3; do for v in 0 1; do
+  echo "== MEGATTS2_LN_FUSE=$v"
+  MEGATTS2_LN_FUSE=$v timeout 600 python tools/time_stages.py --reps 3 2>&1 | grep -A13 "pass 2" | grep -E "adm|plm|launches|full"
+done; done 2>&1 | tee gpurun_out/r2h2_ln_fuse_ab.log
