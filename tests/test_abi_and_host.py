@@ -337,3 +337,11 @@ def test_shard_bounds_properties_hypothesis():
         flat = sorted(i for p in parts for i in p)
         assert len(parts) == world and flat == list(range(len(costs)))               # a partition of the items
     check_cost()
+
+
+def test_graft_entry_build_runs():
+    """The driver's build check: __graft_entry__.build() compiles (a no-op when up to date), loads the library, resolves
+    every declared symbol and checks the ABI version the header and the binding agree on."""
+    import __graft_entry__ as g
+    assert callable(g.build) and callable(g.smoke)
+    g.build()
