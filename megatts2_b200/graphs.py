@@ -57,7 +57,8 @@ class GraphedCall:
             from . import ops
             n0 = ops._lib_launch_count()
             try:
-                with torch.cuda.graph(g):
+                # thread_local: other threads of the process (an NCCL watchdog, a data loader) may call CUDA freely
+                with torch.cuda.graph(g, capture_error_mode="thread_local"):
                     static_out = fn(*static_in)
             except Exception:
                 self.cache[key] = ("eager",)      # capture not possible here (e.g. an allocator or driver restriction)
