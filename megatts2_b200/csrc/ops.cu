@@ -186,7 +186,7 @@ int layernorm(const float* x, int ldx, const float* gamma, const float* beta, co
 // dh = 64 (NI = 2): capped at 80 registers so that three CTAs share an SM (49 vs 53 us at S = 64); the wider heads spill too
 // much under that cap (dh 96: 44 vs 36 us) and keep two CTAs (gpurun call AT, profiles/r2at_attention_regs_ab.log)
 template <int NI, int RW, int NW, int KPL>
-__global__ void __launch_bounds__(NW * 32, (NI == 2 ? 3 : 1)) attn_kernel(const mtts_attn_params p, const int vec, int32_t* ovf) {
+__global__ void __launch_bounds__(NW * 32, (NI == 2 ? 3 : 2)) attn_kernel(const mtts_attn_params p, const int vec, int32_t* ovf) {
   pdl_entry();
   constexpr int DH = 32 * NI;
   constexpr int BQ = RW * NW, BKV = 32 * KPL, NT = NW * 32;
