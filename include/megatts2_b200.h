@@ -25,7 +25,7 @@
 extern "C" {
 #endif
 
-#define MTTS_ABI_VERSION 2
+#define MTTS_ABI_VERSION 3
 
 typedef enum {
   MTTS_OK = 0,
@@ -64,6 +64,12 @@ int mtts_tc_overflow_bind(int32_t* flag_dev);
  * size their grids from it, so work enqueued on two streams can share the device (the prompt re-vocode of Megatts.forward
  * runs beside the latency-bound AR loops). */
 int mtts_set_sm_limit(int32_t n_sms);
+/* Launch policy of the calling host thread while two streams share the device: SM budget (as above), whether the dense
+ * layers may run as CTA pairs (cta_group::2 clusters need two free SMs of one TPC), and whether launches carry the
+ * programmatic-dependent-launch attribute (a long kernel's successor would otherwise be scheduled early onto the SMs left
+ * free for the other stream).  (0, 1, 1) restores the defaults.  Megatts.synthesize uses it to re-vocode the prompt
+ * (models/megatts2.py:371-372 of the reference) beside the MRTE + ADM stages. */
+int mtts_set_launch_policy(int32_t sm_limit, int32_t allow_pairs, int32_t allow_pdl);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };

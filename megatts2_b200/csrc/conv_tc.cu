@@ -761,8 +761,23 @@ int cur_device() {
 // grids from it, so two streams can share the device: the vocoder pass that re-vocodes the prompt runs on a side stream
 // with a reduced budget while the latency-bound AR loops use the SMs it leaves free (models/megatts2.py).
 static thread_local int g_sm_limit = 0;
+static thread_local bool g_pairs_off = false;
 int set_sm_limit(int n) {
   g_sm_limit = n > 0 ? n : 0;
+  return 0;
+}
+// Launch policy of the calling host thread while two streams share the device (models/megatts2.py, the prompt re-vocode beside
+// the MRTE + ADM stages).  Three rules make the sharing work; without any one of them the short launches of one stream queue
+// behind ~1 ms persistent CTAs of the other (the budget-only form measured 447 ... 660 ms against 421 ms sequential,
+// profiles/r2j_revocode_overlap_sweep.log):
+//  * the budgets of the two streams add up to the device (a persistent grid sized for all SMs waits for the other stream's CTAs);
+//  * no programmatic dependent launch on the stream with the long kernels: its NEXT kernel's CTAs would be scheduled early onto
+//    the SMs left free for the other stream and sit there in griddepcontrol.wait until the current kernel has finished;
+//  * no CTA pairs on the stream with the short kernels: the long stream's single CTAs leave free SMs, not free SM pairs.
+int set_launch_policy(int sm_limit, int allow_pairs, int allow_pdl) {
+  g_sm_limit = sm_limit > 0 ? sm_limit : 0;
+  g_pairs_off = allow_pairs == 0;
+  set_thread_pdl(allow_pdl != 0);
   return 0;
 }
 int cur_device_sms() {
@@ -1010,7 +1025,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
   // (256-row tiles waste more of the last tile), so pairs are used for k = 1 only.
   if (env.swb64) SWB = 64;
   bool pair = false;
-  if (env.pair_mode && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || env.pair_mode >= 3)) {
+  if (env.pair_mode && !g_pairs_off && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || env.pair_mode >= 3)) {
     const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
     pair = t256 >= (int64_t)(sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
@@ -1026,7 +1041,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
   // 0.453 ms (its tiles are paced by the epilogue, not by MMA issue; four accumulator buffers instead of two change nothing
   // either: call T) - so pairs are the default for the C = 64 stage only (MEGATTS2_TC_HALO_PAIR = 0 | 1 | 2)
   bool halo_pair = false;
-  if (halo_form && (env.halo_pair >= 2 || (env.halo_pair == 1 && SWB == 128))) {
+  if (halo_form && !g_pairs_off && (env.halo_pair >= 2 || (env.halo_pair == 1 && SWB == 128))) {
     const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256);
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
     halo_pair = t256 >= (int64_t)(sms / 2) * 2 && eff256 >= 0.9 * eff128;

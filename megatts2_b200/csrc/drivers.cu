@@ -875,6 +875,9 @@ int mtts_split_planes_f32(const float* x, int32_t ldx, int64_t rows, int32_t C, 
 int mtts_tc_overflow_bind(int32_t* flag_dev) { return tc_overflow_bind(flag_dev); }
 int mtts_set_attention_pair_min(int32_t min_len) { return set_attention_pair_min(min_len); }
 int mtts_set_sm_limit(int32_t n_sms) { return set_sm_limit(n_sms); }
+int mtts_set_launch_policy(int32_t sm_limit, int32_t allow_pairs, int32_t allow_pdl) {
+  return set_launch_policy(sm_limit, allow_pairs, allow_pdl);
+}
 
 int64_t mtts_plm_infer_workspace_bytes(const mtts_plm* m, int32_t B, int32_t T) { return plm_ws_floats(m, B, T) * 4 + 8192; }
 int mtts_plm_infer_f32(const mtts_plm* m, const float* tc_latent, int64_t tc_sb, int32_t tc_ld, int32_t B, int32_t T,

@@ -371,6 +371,41 @@ def workspace(nbytes, device):
     return buf
 
 
+# ------------------------------------------------------------------------------ launch policy
+_policy = (0, 1, 1)      # (SM budget, CTA pairs allowed, PDL allowed) of this host thread's launches; (0, 1, 1) = defaults
+
+
+def launch_policy_now():
+    """The policy in force (part of the CUDA-graph keys: a captured graph has its grid sizes baked in)."""
+    return _policy
+
+
+class launch_policy:
+    """``with ops.launch_policy(sm_limit, pairs=..., pdl=...)``: the enclosed enqueues size their persistent grids for
+    ``sm_limit`` SMs, optionally without CTA pairs / programmatic dependent launch (include/megatts2_b200.h,
+    mtts_set_launch_policy).  Single host thread, like the reference's callers."""
+
+    def __init__(self, sm_limit, pairs=True, pdl=True):
+        self.new = (int(sm_limit), int(bool(pairs)), int(bool(pdl)))
+
+    def __enter__(self):
+        global _policy
+        self.old = _policy
+        _policy = self.new
+        L.check(L.lib().mtts_set_launch_policy(*self.new))
+        return self
+
+    def __exit__(self, *exc):
+        global _policy
+        _policy = self.old
+        L.lib().mtts_set_launch_policy(*self.old)
+        return False
+
+
+def sm_count(device):
+    return torch.cuda.get_device_properties(device).multi_processor_count
+
+
 def _lib_launch_count():
     return int(L.lib().mtts_launch_count())
 

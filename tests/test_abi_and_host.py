@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(raw, s), f"missing export {s}"
         assert s in L.SIGNATURES, f"{s} has no ctypes signature"
     assert set(L.SIGNATURES) == set(syms)
-    assert lib.mtts_abi_version() == L.ABI_VERSION == 2
+    assert lib.mtts_abi_version() == L.ABI_VERSION == 3
     assert lib.mtts_launch_count() == 0
 
 

@@ -503,6 +503,39 @@ def test_prompt_revocode_and_synthesize_many(weights_cpu):
     assert torch.equal(w[0, :, :48 * 256], pw[0, :, :48 * 256]) and float(w[0, :, 48 * 256:].abs().max()) == 0.0
 
 
+def test_overlapped_prompt_revocode(weights_cpu):
+    """Megatts._synthesize with the prompt re-vocode on a side stream (SM budget V) beside MRTE + ADM on the remaining SMs
+    (ops.launch_policy: complementary budgets, no PDL on the vocoder's stream, no CTA pairs on the AR stream): the waveform of
+    the prompt is bit-identical to the sequential form, ids / durations equal, through eager, capture and replay passes; the
+    policy is restored afterwards."""
+    from megatts2_b200 import ops
+    tts = helpers.build_megatts(weights_cpu("g"), weights_cpu("plm"), weights_cpu("adm"), weights_cpu("hifigan"), DEV)
+    B, Tp, Tm = 6, 24, 64
+    phone = torch.randint(0, 320, (B, Tp), generator=gen(71)).to(DEV)
+    melp = (torch.randn(B, Tm, 80, generator=gen(72)) * 2 - 4).to(DEV)
+    forced = torch.randint(1, 4, (B, Tp), generator=gen(73)).to(torch.int32)
+    forced[:, -1] += (forced.sum(1).max() - forced.sum(1)).to(torch.int32)          # equal totals: one vocoder group
+    forced = forced.to(DEV)
+    seq = tts.synthesize(phone, melp, forced_durations=forced, prompt_mels=melp, return_intermediates=True, overlap_prompt=False)
+    n_p = 256 * (Tm + 10)
+    keys = ("MEGATTS2_REVOCODE_SMS", "MEGATTS2_REVOCODE_FRAC", "MEGATTS2_REVOCODE_FROM")
+    saved = {k: os.environ.get(k) for k in keys}
+    try:
+        for sms, frac, start in (("100", "1.0", "mrte"), ("116", "0.5", "adm"), ("0", "1.0", "mrte")):
+            os.environ.update({keys[0]: sms, keys[1]: frac, keys[2]: start})
+            for _ in range(3):      # eager, graph capture, replay
+                ov = tts.synthesize(phone, melp, forced_durations=forced, prompt_mels=melp, return_intermediates=True,
+                                    overlap_prompt=True)
+                assert ops.launch_policy_now() == (0, 1, 1)
+                assert torch.equal(ov["wav"][..., :n_p], seq["wav"][..., :n_p])
+                assert torch.equal(ov["dt"], seq["dt"]) and torch.equal(ov["p_codes"], seq["p_codes"])
+                assert maxerr(ov["tc_latent"], seq["tc_latent"]) < 1e-4
+                assert maxerr(ov["wav"], seq["wav"]) < 1e-3
+    finally:
+        for k, v in saved.items():
+            os.environ.pop(k, None) if v is None else os.environ.__setitem__(k, v)
+
+
 def test_graph_replay_matches_eager(PLM, ADM):
     """The AR drivers replayed from a CUDA graph (megatts2_b200/graphs.py: eager call, capture, replays) give the eager
     enqueue's ids / durations bit for bit, for new inputs too, and the replayed kernels are counted."""
