@@ -799,7 +799,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int halo_pair; };
+struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int halo_pair; int model; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -819,6 +819,10 @@ static const CtcEnv& ctc_env() {
     e.halo_bo = be ? atoi(be) : 0;
     const char* hp = getenv("MEGATTS2_TC_HALO_PAIR");
     e.halo_pair = hp ? atoi(hp) : 1;          // 0 off, 1 = the C = 64 stage only (default), 2 = C = 32 too
+    // dense-layer dispatch: 0 = tile width by grid fill (rounds 1-2), 1 = tile width by modelled cost (default), 2 = tile
+    // width, K split and pairing all by modelled cost (experimental: measured equal to 1 overall, see conv_tc())
+    const char* mo = getenv("MEGATTS2_TC_MODEL");
+    e.model = mo ? atoi(mo) : 1;
     return e;
   }();
   return env;
@@ -984,52 +988,107 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
     MTTS_CHECK_LAUNCH();
   }
   int SWB = p.Cin >= 64 ? 128 : 64;
-  // N-tile width: the widest tile that still gives every SM a tile; under-filled grids are latency-bound
-  // (one 128x128xK tile per CTA is paced by TMA round trips, not by the tensor pipe), so narrow tiles win there
   int BN = 32;
-  if (SWB == 128) {
-    const int64_t mt = (int64_t)p.B * cdiv64(p.Tout, 128);
+  int splits = 1;
+  bool pair = false;
+  const bool pairs_ok = env.pair_mode && !g_pairs_off;
+  if (env.model >= 2 && p.k == 1 && SWB == 128 && !env.swb64) {
+    // EXPERIMENTAL (MEGATTS2_TC_MODEL=2): tile width, K split and CTA pairing of a dense layer chosen together by modelled
+    // launch cost.  A persistent CTA walks ceil(items / SMs) work items of ceil(nk / sk) K-slabs each; a slab is 4 k-steps x
+    // 3 | 6 MMAs at 65 cycles (N = 128) or 55 (the per-instruction floor, N <= 64: tools/microbench/mma_floor2.cu).  Measured
+    // per AR step against the fill heuristics (gpurun call TM, profiles/r2tm_ar_curves.log): -0.25 ms on PLM steps 19 ... 28
+    // (which mode 1 below keeps), but +0.06 ... 0.11 ms on steps 9 ... 14, where it prefers 64-wide tiles to a 3-way K split
+    // whose reduction rides on the LayerNorm launch, and +0.02 ... 0.06 ms on steps 45 ... 54 (2-way split of FF2): the model
+    // underrates wide-tile splits.  Split-K partial sums are added in split order, so results never depend on timing.
+    const int64_t rows = (int64_t)p.B * p.Tout;
+    const int64_t mt = (int64_t)p.B * cdiv64(p.Tout, 128), mt2 = (int64_t)p.B * cdiv64(p.Tout, 256);
+    const int nk = (p.Cin + 63) / 64;
+    const double mm = 4.0 * (np == 2 ? 3 : 6);                       // MMAs per 64-wide K-slab
+    double best = 1e30;
     const int cands[3] = {128, 64, 32};
     for (int i = 0; i < 3; ++i) {
       if (cands[i] > p.Cout) continue;
-      BN = cands[i];
-      if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(sms * 4) / 5) break;
+      const double c = (double)cdiv64(mt * cdiv64(p.Cout, cands[i]), sms) * nk * mm * (cands[i] == 128 ? 65.0 : 55.0);
+      if (c <= best) { best = c; BN = cands[i]; }      // ties (same number of waves at the 55-cycle floor) go to the narrower
+    }                                                   // tile: more SMs stream the weights
+    if (pairs_ok && p.Cout % 128 == 0) {
+      // a pair runs 256 rows per item in the time a single CTA runs 128 (each SM's tensor core does its own half); it reads a
+      // quarter fewer operand bytes per FLOP (+1..3 % measured on full grids), so it wins ties against single CTAs
+      const double c = 0.98 * (double)cdiv64(mt2 * (p.Cout / 128), sms / 2) * nk * mm * 65.0;
+      if (c <= best) { best = c; BN = 128; pair = true; }
     }
-  }
-  // split-K for dense layers with too few output tiles to fill the GPU (the early steps of the AR loops, the N = 1024
-  // layers up to ~30 steps): narrow tiles would pay the 55-cycle minimum per MMA (tools/microbench/mma_floor.cu) on
-  // every k-step, so K is split across CTAs at full tile width instead and a second kernel reduces the partials
-  int splits = 1;
-  {
-    const int64_t rows = (int64_t)p.B * p.Tout;
-    const int64_t t128 = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, 128);
-    const int nk = (p.Cin + 63) / 64;
-    if (env.splitk && SWB == 128 && p.k == 1 && p.out_shift == 0 && p.tc_partial && p.Cout >= 128 &&
-        t128 < (int64_t)(sms * 4) / 5) {
-      int sk = (int)(sms / t128);
-      if (sk > env.sk_max) sk = env.sk_max;
-      if (sk > nk / 2) sk = nk / 2;
-      if (sk >= 2 && (int64_t)sk * rows * p.Cout * 4 <= p.tc_partial_bytes) {
-        const int64_t tiles_bn = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, BN);
-        const double waves = (double)cdiv64(tiles_bn, sms);
-        const double mmas = 4.0 * (2 * np);                                                 // MMAs per 64-wide K-slab
-        const double cost_now = waves * nk * mmas * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
-        const double cost_split = (double)cdiv64(nk, sk) * mmas * 65.0 + 9000.0;             // + reduction kernel
-        if (cost_split < env.margin * cost_now) { splits = sk; BN = 128; }
+    if (env.splitk && p.out_shift == 0 && p.tc_partial && p.Cout >= 128) {
+      const bool ln_rides = ln && ln->po.p && p.y && !p.tc_out_planes && (p.Cout == 1024 || p.Cout == 768 || p.Cout == 512 || p.Cout == 384);
+      const int64_t t128 = mt * cdiv64(p.Cout, 128);
+      for (int sk = 2; sk <= env.sk_max && sk <= nk / 2; ++sk) {
+        if ((int64_t)sk * rows * p.Cout * 4 > p.tc_partial_bytes) break;
+        // + the reduction: its own launch (~4 us) unless it replaces the LayerNorm launch (~1 us extra), + the partial sums
+        // written and read back through L2 (~4 TB/s, writes counted half)
+        const double red = (ln_rides ? 1800.0 : 7300.0) + (double)sk * rows * p.Cout * 4.0 * 6.9e-4;
+        const double c = (double)cdiv64(t128 * sk, sms) * (double)cdiv64(nk, sk) * mm * 65.0 + red;
+        if (c < best) { best = c; BN = 128; pair = false; splits = sk; }
       }
     }
-  }
-  // CTA pairs (cta_group::2): two SMs share one 256 x 128 tile; each stages its own 128 activation rows and HALF of the
-  // weight tile, so a quarter fewer bytes cross L2 -> SM and a quarter fewer operand bytes are read from shared memory
-  // per FLOP.  Measured (tools/bench_tc_shapes.py): +1..3 % on the dense layers, -5 % on the ragged-T convolutions
-  // (256-row tiles waste more of the last tile), so pairs are used for k = 1 only.
-  if (env.swb64) SWB = 64;
-  bool pair = false;
-  if (env.pair_mode && !g_pairs_off && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || env.pair_mode >= 3)) {
-    const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
-    const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
-    pair = t256 >= (int64_t)(sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
-    if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs
+    if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs (diagnostics)
+  } else {
+    // N-tile width.  A persistent CTA walks ceil(tiles / SMs) tiles of nk K-slabs; a slab's MMAs cost 65 cycles each at
+    // N = 128 and 55 (the per-instruction floor) at N <= 64, so the width with the cheapest walk wins and ties go to the
+    // narrower tile (under-filled grids are latency-bound: more SMs stream the weights).  The earlier rule - the widest tile
+    // that still gives 80 % of the SMs a tile - ran e.g. the PLM FF2 layer of steps 19 ... 28 as 160 tiles of N = 64 on 148 SMs,
+    // two waves, where 80 tiles of N = 128 take one: -0.25 ms per step there, -0.03 ms on ADM steps 25 ... 38 (gpurun call TM,
+    // profiles/r2tm_ar_curves.log; MEGATTS2_TC_MODEL=0 restores it).  Convolutions (k > 1) keep the fill rule: their grids are
+    // hundreds of waves deep and the halo form wants BN == Cout.
+    if (SWB == 128) {
+      const int64_t mt = (int64_t)p.B * cdiv64(p.Tout, 128);
+      const int cands[3] = {128, 64, 32};
+      if (env.model >= 1 && p.k == 1) {
+        int64_t best = INT64_MAX;
+        for (int i = 0; i < 3; ++i) {
+          if (cands[i] > p.Cout) continue;
+          const int64_t c = cdiv64(mt * cdiv64(p.Cout, cands[i]), sms) * (cands[i] == 128 ? 65 : 55);
+          if (c <= best) { best = c; BN = cands[i]; }
+        }
+      } else {
+        for (int i = 0; i < 3; ++i) {
+          if (cands[i] > p.Cout) continue;
+          BN = cands[i];
+          if (mt * cdiv64(p.Cout, cands[i]) >= (int64_t)(sms * 4) / 5) break;
+        }
+      }
+    }
+    // split-K for dense layers with too few output tiles to fill the GPU (the early steps of the AR loops, the N = 1024
+    // layers up to ~30 steps): narrow tiles would pay the 55-cycle minimum per MMA (tools/microbench/mma_floor.cu) on
+    // every k-step, so K is split across CTAs at full tile width instead and a second kernel reduces the partials
+    {
+      const int64_t rows = (int64_t)p.B * p.Tout;
+      const int64_t t128 = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, 128);
+      const int nk = (p.Cin + 63) / 64;
+      if (env.splitk && SWB == 128 && p.k == 1 && p.out_shift == 0 && p.tc_partial && p.Cout >= 128 &&
+          t128 < (int64_t)(sms * 4) / 5) {
+        int sk = (int)(sms / t128);
+        if (sk > env.sk_max) sk = env.sk_max;
+        if (sk > nk / 2) sk = nk / 2;
+        if (sk >= 2 && (int64_t)sk * rows * p.Cout * 4 <= p.tc_partial_bytes) {
+          const int64_t tiles_bn = (int64_t)p.B * cdiv64(p.Tout, 128) * cdiv64(p.Cout, BN);
+          const double waves = (double)cdiv64(tiles_bn, sms);
+          const double mmas = 4.0 * (2 * np);                                                 // MMAs per 64-wide K-slab
+          const double cost_now = waves * nk * mmas * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
+          const double cost_split = (double)cdiv64(nk, sk) * mmas * 65.0 + 9000.0;             // + reduction kernel
+          if (cost_split < env.margin * cost_now) { splits = sk; BN = 128; }
+        }
+      }
+    }
+    // CTA pairs (cta_group::2): two SMs share one 256 x 128 tile; each stages its own 128 activation rows and HALF of the
+    // weight tile, so a quarter fewer bytes cross L2 -> SM and a quarter fewer operand bytes are read from shared memory
+    // per FLOP.  Measured (tools/bench_tc_shapes.py): +1..3 % on the dense layers, -5 % on the ragged-T convolutions
+    // (256-row tiles waste more of the last tile), so pairs are used for k = 1 only.
+    if (env.swb64) SWB = 64;
+    if (pairs_ok && splits == 1 && BN == 128 && p.Cout % 128 == 0 && (p.k == 1 || env.pair_mode >= 3)) {
+      const int64_t t256 = (int64_t)p.B * cdiv64(p.Tout, 256) * (p.Cout / 128);
+      const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
+      pair = t256 >= (int64_t)(sms / 2) * 4 / 5 && eff256 >= 0.9 * eff128;
+      if (pair && (env.pair_mode == 2 || env.pair_mode == 4)) SWB = 64;      // 32-wide K-slabs
+    }
   }
   // halo form: one K-slab per tap (Cin <= SWB / 2), the activation tile + halo fits the 192-row buffer
   const bool halo_form = env.halo && !pair && splits == 1 && p.out_shift == 0 && p.k > 1 && p.Cin <= SWB / 2 &&
