@@ -43,6 +43,25 @@ def test_error_reporting_without_gpu():
         L.check(lib.mtts_attention_f32(None, None))
 
 
+def test_launch_policy_is_scoped_and_restored():
+    """ops.launch_policy (SM budget, CTA pairs, PDL of the calling thread's launches; host state only, no CUDA call): nests,
+    restores on exit and on exceptions, and is part of the CUDA-graph keys of the AR drivers."""
+    from megatts2_b200 import ops
+    assert ops.launch_policy_now() == (0, 1, 1)
+    with ops.launch_policy(100, pairs=True, pdl=False):
+        assert ops.launch_policy_now() == (100, 1, 0)
+        with ops.launch_policy(48, pairs=False):
+            assert ops.launch_policy_now() == (48, 0, 1)
+        assert ops.launch_policy_now() == (100, 1, 0)
+    assert ops.launch_policy_now() == (0, 1, 1)
+    with pytest.raises(RuntimeError):
+        with ops.launch_policy(64):
+            raise RuntimeError("boom")
+    assert ops.launch_policy_now() == (0, 1, 1)
+    src = open(os.path.join(ROOT, "megatts2_b200", "models", "megatts2.py")).read()
+    assert src.count("ops.launch_policy_now()") >= 2          # MegaPLM.infer and MegaADM.infer graph keys
+
+
 def test_no_cpu_fallback():
     from megatts2_b200 import _lib as L
     from megatts2_b200 import ops
