@@ -70,6 +70,12 @@ int mtts_set_sm_limit(int32_t n_sms);
  * free for the other stream).  (0, 1, 1) restores the defaults.  Megatts.synthesize uses it to re-vocode the prompt
  * (models/megatts2.py:371-372 of the reference) beside the MRTE + ADM stages. */
 int mtts_set_launch_policy(int32_t sm_limit, int32_t allow_pairs, int32_t allow_pdl);
+/* Diagnostics (host only, no CUDA call): the launch plan the tap-GEMM dispatcher picks for a stride-1 layer of this shape
+ * (B x T output rows, k taps) on n_sms SMs, with partial_bytes of split-K partial-sum space and, if ln_rides, a LayerNorm
+ * that the split's reduction can carry.  out5 = {N-tile width, K splits, CTA pair, halo form (0 | 1 | 2 = as a pair),
+ * K-slab bytes}. */
+int mtts_tc_plan_query(int32_t n_sms, int32_t B, int32_t T, int32_t Cin, int32_t Cout, int32_t k, int32_t dil, int32_t fmt,
+                       int64_t partial_bytes, int32_t ln_rides, int32_t* out5);
 
 /* activation / padding codes */
 enum { MTTS_ACT_NONE = 0, MTTS_ACT_RELU = 1, MTTS_ACT_LEAKY = 2, MTTS_ACT_TANH = 3 };

@@ -968,25 +968,12 @@ bool conv_tc_eligible(const mtts_conv_params& p) {
   return 3 * rows * p.Cin * 2 + 2048 <= p.tc_scratch_bytes;
 }
 
-int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
-  if (ln) ln->done = 0;
-  const CtcEnv& env = ctc_env();
-  const int sms = cur_device_sms();
-  const int fmt = p.tc_fmt;
-  const int np = fmt == MTTS_TC_F16X2 ? 2 : 3;
-  int32_t* ovf = tc_ovf_ptr();
+// The launch plan of one tap-GEMM: K-slab width, N-tile width, K splits, CTA pairing, halo form.  A pure function of the shape,
+// the SM budget and the (read-once) tuning switches, so the policy can be queried and tested without a GPU
+// (mtts_tc_plan_query, tests/test_abi_and_host.py).
+struct TcPlan { int SWB, BN, splits; bool pair, halo_form, halo_pair; };
+static TcPlan tc_plan(const CtcEnv& env, int sms, const mtts_conv_params& p, int np, bool ln_rides) {
   const int halo = p.dil * (p.k - 1);
-  const int hl = p.pad, Tp = p.Tout + halo;
-  const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : (p.tc_in_tp > 0 ? p.tc_in_tp : Tp);     // descriptor rows (>= Tp)
-  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
-  const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
-  if (!p.tc_presplit) {
-    const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
-    launch_k(split_pad_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
-                                                                   p.pad_mode, p.pre_act, p.pre_slope, planes, plane_stride,
-                                                                   total4, fmt, ovf);
-    MTTS_CHECK_LAUNCH();
-  }
   int SWB = p.Cin >= 64 ? 128 : 64;
   int BN = 32;
   int splits = 1;
@@ -1018,8 +1005,7 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
       if (c <= best) { best = c; BN = 128; pair = true; }
     }
     if (env.splitk && p.out_shift == 0 && p.tc_partial && p.Cout >= 128) {
-      const bool ln_rides = ln && ln->po.p && p.y && !p.tc_out_planes && (p.Cout == 1024 || p.Cout == 768 || p.Cout == 512 || p.Cout == 384);
-      const int64_t t128 = mt * cdiv64(p.Cout, 128);
+            const int64_t t128 = mt * cdiv64(p.Cout, 128);
       for (int sk = 2; sk <= env.sk_max && sk <= nk / 2; ++sk) {
         if ((int64_t)sk * rows * p.Cout * 4 > p.tc_partial_bytes) break;
         // + the reduction: its own launch (~4 us) unless it replaces the LayerNorm launch (~1 us extra), + the partial sums
@@ -1105,6 +1091,35 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
     const double eff128 = (double)p.Tout / (128.0 * cdiv64(p.Tout, 128)), eff256 = (double)p.Tout / (256.0 * cdiv64(p.Tout, 256));
     halo_pair = t256 >= (int64_t)(sms / 2) * 2 && eff256 >= 0.9 * eff128;
   }
+  TcPlan pl;
+  pl.SWB = SWB; pl.BN = BN; pl.splits = splits; pl.pair = pair; pl.halo_form = halo_form; pl.halo_pair = halo_pair;
+  return pl;
+}
+
+int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
+  if (ln) ln->done = 0;
+  const CtcEnv& env = ctc_env();
+  const int sms = cur_device_sms();
+  const int fmt = p.tc_fmt;
+  const int np = fmt == MTTS_TC_F16X2 ? 2 : 3;
+  int32_t* ovf = tc_ovf_ptr();
+  const int halo = p.dil * (p.k - 1);
+  const int hl = p.pad, Tp = p.Tout + halo;
+  const int64_t Tp_map = p.tc_rows_cap > 0 ? p.tc_rows_cap : (p.tc_in_tp > 0 ? p.tc_in_tp : Tp);     // descriptor rows (>= Tp)
+  __nv_bfloat16* planes = reinterpret_cast<__nv_bfloat16*>((((uintptr_t)p.tc_scratch) + 1023) & ~(uintptr_t)1023);
+  const int64_t plane_stride = (int64_t)p.B * Tp_map * p.Cin;
+  if (!p.tc_presplit) {
+    const int64_t total4 = (int64_t)p.B * Tp * p.Cin / 4;
+    launch_k(split_pad_kernel, (unsigned)cdiv64(total4, 256), 256, 0, st, p.x, p.x_batch_stride, p.ldx, p.Tin, p.Cin, hl, Tp,
+                                                                   p.pad_mode, p.pre_act, p.pre_slope, planes, plane_stride,
+                                                                   total4, fmt, ovf);
+    MTTS_CHECK_LAUNCH();
+  }
+  // the reduction of a split launch can carry the LayerNorm the caller asked for when a row is 3 / 4 / 6 / 8 x 128 wide
+  const bool ln_rides = ln && ln->po.p && p.y && !p.tc_out_planes && (p.Cout == 1024 || p.Cout == 768 || p.Cout == 512 || p.Cout == 384);
+  const TcPlan pl = tc_plan(env, sms, p, np, ln_rides);
+  const int SWB = pl.SWB, BN = pl.BN, splits = pl.splits;
+  const bool pair = pl.pair, halo_form = pl.halo_form, halo_pair = pl.halo_pair;
   const int b_rows = (pair || halo_pair) ? BN / 2 : BN;
   ConvTcMaps maps;
   for (int q = 0; q < np; ++q) {
@@ -1152,6 +1167,22 @@ int conv_tc(const mtts_conv_params& p, cudaStream_t st, LnFuse* ln) {
     return 0;
   }
   return np == 2 ? conv_tc_dispatch<2>(maps, a, BN, SWB, pair, st) : conv_tc_dispatch<3>(maps, a, BN, SWB, pair, st);
+}
+
+// diagnostics: the plan conv_tc() would pick for a stride-1 tap-GEMM of this shape on `sms` SMs; out = {BN, splits, pair,
+// halo form (0 | 1 | 2 = as a CTA pair), K-slab bytes}
+int tc_plan_query(int sms, int B, int T, int Cin, int Cout, int k, int dil, int fmt, int64_t partial_bytes, int ln_rides, int32_t* out5) {
+  MTTS_REQUIRE(out5 && sms > 0 && B > 0 && T > 0 && Cin > 0 && Cout > 0 && k > 0 && dil > 0, "bad arguments");
+  MTTS_REQUIRE(fmt == MTTS_TC_BF16X3 || fmt == MTTS_TC_F16X2, "unknown operand format");
+  mtts_conv_params p;
+  memset(&p, 0, sizeof(p));
+  p.B = B; p.Tin = T + dil * (k - 1); p.Tout = T; p.Cin = Cin; p.Cout = Cout; p.k = k; p.stride = 1; p.dil = dil;
+  static float dummy;
+  p.y = &dummy;
+  if (partial_bytes > 0) { p.tc_partial = &dummy; p.tc_partial_bytes = partial_bytes; }
+  const TcPlan pl = tc_plan(ctc_env(), sms, p, fmt == MTTS_TC_F16X2 ? 2 : 3, ln_rides != 0);
+  out5[0] = pl.BN; out5[1] = pl.splits; out5[2] = pl.pair ? 1 : 0; out5[3] = pl.halo_form ? (pl.halo_pair ? 2 : 1) : 0; out5[4] = pl.SWB;
+  return 0;
 }
 
 // fp32 (B, T, C) -> padded operand planes (B, hl + T + hr, C) at the 1024-byte-aligned start of `planes_base`
