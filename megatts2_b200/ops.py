@@ -7,6 +7,7 @@ convert at their boundary.
 """
 import ctypes as C
 import math
+import threading
 
 import torch
 
@@ -372,33 +373,32 @@ def workspace(nbytes, device):
 
 
 # ------------------------------------------------------------------------------ launch policy
-_policy = (0, 1, 1)      # (SM budget, CTA pairs allowed, PDL allowed) of this host thread's launches; (0, 1, 1) = defaults
+_tls = threading.local()      # the C side keeps the policy per host thread (thread_local), so does this mirror
 
 
 def launch_policy_now():
-    """The policy in force (part of the CUDA-graph keys: a captured graph has its grid sizes baked in)."""
-    return _policy
+    """(SM budget, CTA pairs allowed, PDL allowed) of the calling thread's launches; (0, 1, 1) = defaults.  Part of the
+    CUDA-graph keys: a captured graph has its grid sizes baked in."""
+    return getattr(_tls, "policy", (0, 1, 1))
 
 
 class launch_policy:
-    """``with ops.launch_policy(sm_limit, pairs=..., pdl=...)``: the enclosed enqueues size their persistent grids for
-    ``sm_limit`` SMs, optionally without CTA pairs / programmatic dependent launch (include/megatts2_b200.h,
-    mtts_set_launch_policy).  Single host thread, like the reference's callers."""
+    """``with ops.launch_policy(sm_limit, pairs=..., pdl=...)``: the enclosed enqueues of this thread size their persistent
+    grids for ``sm_limit`` SMs, optionally without CTA pairs / programmatic dependent launch (include/megatts2_b200.h,
+    mtts_set_launch_policy).  Restored on exit, also when the body raises."""
 
     def __init__(self, sm_limit, pairs=True, pdl=True):
         self.new = (int(sm_limit), int(bool(pairs)), int(bool(pdl)))
 
     def __enter__(self):
-        global _policy
-        self.old = _policy
-        _policy = self.new
+        self.old = launch_policy_now()
         L.check(L.lib().mtts_set_launch_policy(*self.new))
+        _tls.policy = self.new
         return self
 
     def __exit__(self, *exc):
-        global _policy
-        _policy = self.old
         L.lib().mtts_set_launch_policy(*self.old)
+        _tls.policy = self.old
         return False
 
 
