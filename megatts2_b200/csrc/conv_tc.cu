@@ -799,7 +799,7 @@ int tc_overflow_bind(int32_t* flag) {
 // tuning switches (diagnostics), read ONCE per process: MEGATTS2_TC_SPLITK = 0 disables split-K, _SPLITK_MAX / _SPLITK_MARGIN
 // tune its cost model, MEGATTS2_TC_PAIR = 0 | 1 | 2 | 3 | 4 (0: no CTA pairs, 2 / 4: 32-wide K-slabs, 3 / 4: pairs for convs
 // too), MEGATTS2_TC_SWB64 = 1 forces 64-byte swizzle rows
-struct CtcEnv { bool splitk; int sk_max; double margin; int pair_mode; bool swb64; bool halo; int halo_bo; int halo_pair; int model; };
+struct CtcEnv { bool splitk; int sk_max; double margin; double ln_red; int pair_mode; bool swb64; bool halo; int halo_bo; int halo_pair; int model; };
 static const CtcEnv& ctc_env() {
   static const CtcEnv env = [] {
     CtcEnv e;
@@ -811,6 +811,11 @@ static const CtcEnv& ctc_env() {
     e.splitk = !(ke && ke[0] == '0');
     e.sk_max = me ? atoi(me) : 8;
     e.margin = ge ? atof(ge) : 0.85;
+    // modelled cycles of a reduction that REPLACES the LayerNorm launch that would follow anyway (tc_splitk_reduce_ln_kernel):
+    // 2000 instead of the plain reduction's 9000 makes the out-projection / FF2 layers split up to steps 18 (PLM) / 24 (ADM):
+    // every affected step got faster, PLM -0.4 ms, ADM -1.0 ms per decode (gpurun call LN, profiles/r3d_lncost_curves.log)
+    const char* le = getenv("MEGATTS2_TC_SPLITK_LNCOST");
+    e.ln_red = le ? atof(le) : 2000.0;
     e.pair_mode = pe ? atoi(pe) : 1;
     e.swb64 = se && se[0] == '1';
     const char* he = getenv("MEGATTS2_TC_HALO");          // 0: every tap re-loads its activation tile (the plain form)
@@ -1059,7 +1064,7 @@ static TcPlan tc_plan(const CtcEnv& env, int sms, const mtts_conv_params& p, int
           const double waves = (double)cdiv64(tiles_bn, sms);
           const double mmas = 4.0 * (2 * np);                                                 // MMAs per 64-wide K-slab
           const double cost_now = waves * nk * mmas * (BN == 128 ? 65.0 : 55.0);                // cycles per CTA
-          const double cost_split = (double)cdiv64(nk, sk) * mmas * 65.0 + 9000.0;             // + reduction kernel
+          const double cost_split = (double)cdiv64(nk, sk) * mmas * 65.0 + (ln_rides ? env.ln_red : 9000.0);   // + reduction kernel
           if (cost_split < env.margin * cost_now) { splits = sk; BN = 128; }
         }
       }
