@@ -1003,7 +1003,7 @@ static TcPlan tc_plan(const CtcEnv& env, int sms, const mtts_conv_params& p, int
       const double c = (double)cdiv64(mt * cdiv64(p.Cout, cands[i]), sms) * nk * mm * (cands[i] == 128 ? 65.0 : 55.0);
       if (c <= best) { best = c; BN = cands[i]; }      // ties (same number of waves at the 55-cycle floor) go to the narrower
     }                                                   // tile: more SMs stream the weights
-    if (pairs_ok && p.Cout % 128 == 0) {
+    if (pairs_ok && sms >= 2 && p.Cout % 128 == 0) {
       // a pair runs 256 rows per item in the time a single CTA runs 128 (each SM's tensor core does its own half); it reads a
       // quarter fewer operand bytes per FLOP (+1..3 % measured on full grids), so it wins ties against single CTAs
       const double c = 0.98 * (double)cdiv64(mt2 * (p.Cout / 128), sms / 2) * nk * mm * 65.0;
